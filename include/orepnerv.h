@@ -1,0 +1,190 @@
+/* orepnerv.h — C ABI of liborepnerv.so: the B200 (sm_100a) kernels behind the Online-RepNeRV
+ * frame-fitting hot path.
+ *
+ * The reference (maoqingyu1996/Boosting-Neural-Video-Representation-via-Online-Structural-
+ * Reparameteration) has no FFI: its seam is the Python API in model.py / utils.py.  Every entry
+ * point below names the reference call site (file:line under /root/reference) whose arithmetic
+ * it replaces.  The Python host layer (package dir, `model.py` / `utils.py`) binds these with
+ * ctypes; see INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *  - every function is stream-ordered and asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    never allocates or frees device memory, never synchronises, and is CUDA-graph capturable;
+ *  - return value: 0 = OK, <0 = bad argument / unsupported shape / wrong architecture,
+ *    >0 = cudaError_t;  onr_last_error() returns a thread-local message;
+ *  - activations between kernels are NHWC bf16 with the channel count padded to a multiple of 32
+ *    ("Cp"); parameters, gradients, optimizer state, images and losses are fp32 in the reference's
+ *    own layouts (OIHW / NCHW), so checkpoints stay byte-compatible.
+ */
+#ifndef OREPNERV_H
+#define OREPNERV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONR_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ library / errors */
+int onr_abi_version(void);
+const char* onr_last_error(void);
+/* 0 when the current device is compute capability 10.x (B200); <0 otherwise.  The library has no
+ * other code path: callers must fail loudly when this fails. */
+int onr_check_device(void);
+
+/* ------------------------------------------------------------------ A1+A2: positional encoding + stem
+ * utils.py:121-129 (PositionalEncoding.forward), model.py:174-188, 612-613 (stem MLP + view).
+ * t_norm[B] (fp32 frame index i/N).  Produces embed[B,2L] (fp32, sin/cos interleaved, rounding order
+ * (t*lbase^i)*pi with lbase^i evaluated in double then rounded to fp32 like the reference),
+ * h1[B,hid] = SiLU(W1 e + b1), and the stem output written as NHWC bf16 x0[B,fh,fw,Cp]
+ * (value of reference out[b, c*fh*fw + h*fw + w]), plus dstem[B,fh,fw,Cp] = SiLU'(pre-activation). */
+int onr_pe_stem_fwd(const float* t_norm, int B, float lbase, int levels,
+                    const float* W1, const float* b1, int hid,
+                    const float* W2, const float* b2, int fc_dim, int fh, int fw, int Cp,
+                    float* embed, float* pre1, float* h1,
+                    void* x0_bf16, void* dstem_bf16, void* stream);
+/* Backward of the stem (autograd of model.py:612 through main_train.py:249).
+ * g0[B,fh,fw,Cp] bf16 is dL/d(pre-activation of the 2nd Linear) (SiLU' already applied by the
+ * block-0 dgrad epilogue).  Accumulates (+=) into gW1,gb1,gW2,gb2. */
+int onr_stem_bwd(const void* g0_bf16, int B, const float* embed, int emb_len,
+                 const float* pre1, const float* h1, int hid,
+                 const float* W2, int fc_dim, int fh, int fw, int Cp,
+                 float* gW1, float* gb1, float* gW2, float* gb2,
+                 float* scratch_dh1 /* [B,hid] */, void* stream);
+
+/* ------------------------------------------------------------------ A3: ERB online fold
+ * model.py:450-516 (get_equivalent_kernel_bias, _fuse_1x3_3x1_branch, _fuse_1x1_3x3_1x1_branch).
+ * Inputs are the nine branch tensors in the reference's OIHW layouts.  Outputs:
+ *   K[Cout,Cin,3,3], bias[Cout]  fp32 (reference layout; what switch_to_deploy stores),
+ *   T[Cout,Cin,3,3] fp32 = W2 (x) W1 contraction, kept for the backward,
+ * `Cout` = Cnew*s*s in the reference's PixelShuffle order (c*s*s + i*s + j). */
+int onr_erb_fold_fwd(const float* w3x3, const float* b3x3, const float* w1x3, const float* b1x3,
+                     const float* w3x1, const float* b3x1, const float* w1 /*[2Cin,Cin]*/,
+                     const float* w2 /*[Cout,2Cin,3,3]*/, const float* w3 /*[Cout,Cout]*/,
+                     int Cin, int Cout, float* K, float* bias, float* T, void* stream);
+/* Backward of the fold: scatters dK[Cout,Cin,3,3], dbias[Cout] to the nine branch gradients (+=).
+ * dT is scratch [Cout,Cin,3,3]. */
+int onr_erb_fold_bwd(const float* dK, const float* dbias, const float* w1, const float* w2,
+                     const float* w3, const float* T, int Cin, int Cout,
+                     float* g3x3, float* gb3x3, float* g1x3, float* gb1x3, float* g3x1, float* gb3x1,
+                     float* gw1, float* gw2, float* gw3, float* dT, void* stream);
+
+/* Pack a folded (or vanilla / deploy) OIHW fp32 kernel into the two bf16 implicit-GEMM operand
+ * layouts the convolution kernels consume.  n' = (i*s+j)*Cpo + c  for reference channel
+ * o = c*s*s + i*s + j (nn.PixelShuffle order, model.py:310), Cpo = pad32(Cnew), Cpi = pad32(Cin):
+ *   wf[9][Npad][Cpi]     (fprop:  B operand, K = input channel)        Npad = n_tiles*block_n
+ *   wd[9][Cpi_pad][Nk]   (dgrad:  B operand, K = n', taps flipped)      Nk = s*s*Cpo
+ *   bias_p[Npad]         fp32 bias in n' order (0 in padding)                                   */
+int onr_pack_weights(const float* K, const float* bias, int Cin, int Cnew, int s,
+                     int Npad, int Cpi_rows,
+                     void* wf_bf16, void* wd_bf16, float* bias_p, void* stream);
+/* Inverse for gradients: dKp[Nk][9][Cpi] fp32 (wgrad output, n' order) and dbias_p[Nk] ->
+ * dK[Cout,Cin,3,3], dbias[Cout] in reference layout (overwrites). */
+int onr_unpack_wgrad(const float* dKp, const float* dbias_p, int Cin, int Cnew, int s,
+                     float* dK, float* dbias, void* stream);
+
+/* ------------------------------------------------------------------ A4+A5: block conv3x3 + PixelShuffle + SiLU
+ * model.py:539 / :523 / :520 (F.conv2d 3x3 pad 1) and :567 (up_scale, act).  tcgen05/TMEM implicit
+ * GEMM fed by TMA.  A plan owns only TMA descriptors for fixed buffers; create once, run per step. */
+typedef struct onr_conv_plan onr_conv_plan;
+
+enum { ONR_CONV_FPROP_TRAIN = 0, ONR_CONV_FPROP_INFER = 1, ONR_CONV_DGRAD = 2 };
+
+typedef struct {
+    int kind;        /* ONR_CONV_* */
+    int B, H, W;     /* GEMM pixel grid = the conv's input grid */
+    /* A operand: NHWC bf16 [B][H*a_s][W*a_s][a_cp], read through the "un-shuffled" view
+       (a_s = 1: plain activation for fprop; a_s = s: dZ of this block for dgrad). */
+    const void* a; int a_cp; int a_s;
+    /* B operand: packed weights [9][n_rows][k_tap] bf16, k_tap = a_s*a_s*a_cp */
+    const void* w; int n_rows;
+    int n_total;     /* valid GEMM N (multiple of 32) = out_s*out_s*out_cp */
+    /* outputs: NHWC bf16 [B][H*out_s][W*out_s][out_cp] written through the shuffled view */
+    void* out; int out_cp; int out_s;
+    void* out_d;     /* FPROP_TRAIN: SiLU'(z) in the same layout as out */
+    const float* bias_p;  /* FPROP_*: [n_total] in n' order */
+    const void* dmul;     /* DGRAD: NHWC bf16 [B][H][W][n_total] multiplied into the result */
+} onr_conv_desc;
+
+int onr_conv_plan_create(onr_conv_plan** plan, const onr_conv_desc* desc);
+int onr_conv_plan_run(const onr_conv_plan* plan, void* stream);
+void onr_conv_plan_destroy(onr_conv_plan* plan);
+/* block_n / n_tiles the plan will use for a given N, so callers can size packed weights. */
+int onr_conv_tile_n(int n_total, int* block_n, int* n_tiles);
+
+/* A8 (wgrad): dKp[Nk][9][Cpi] (fp32, += via red.global) from x NHWC [B][H][W][Cpi] and
+ * dz NHWC [B][H*s][W*s][Cpo] (read through the un-shuffled view).  tcgen05 with MN-major operands. */
+typedef struct onr_wgrad_plan onr_wgrad_plan;
+typedef struct {
+    int B, H, W;
+    const void* x; int x_cp;
+    const void* dz; int dz_cp; int s;
+    float* dKp;      /* [s*s*dz_cp][9][x_cp], must be zeroed by the caller before the run */
+    float* dbias_p;  /* [s*s*dz_cp], zeroed by the caller; column sums of dz */
+} onr_wgrad_desc;
+int onr_wgrad_plan_create(onr_wgrad_plan** plan, const onr_wgrad_desc* desc);
+int onr_wgrad_plan_run(const onr_wgrad_plan* plan, void* stream);
+void onr_wgrad_plan_destroy(onr_wgrad_plan* plan);
+
+/* Plain SIMT versions of the three convolution passes on the same layouts.  Test infrastructure
+ * for on-device cross-checks at sizes the CPU oracle cannot reach; not used by the product path. */
+int onr_simt_conv(const onr_conv_desc* desc, void* stream);
+int onr_simt_wgrad(const onr_wgrad_desc* desc, void* stream);
+
+/* Layout converters at the module boundary (NeRVBlock.forward takes/returns NCHW fp32). */
+int onr_nchw_to_nhwc_bf16(const float* src, int B, int C, int H, int W, int Cp, void* dst, void* stream);
+int onr_nhwc_bf16_to_nchw(const void* src, int B, int C, int H, int W, int Cp, float* dst, void* stream);
+
+/* ------------------------------------------------------------------ A6: RGB head
+ * model.py:601, :620-623: 1x1 conv C->3 + bias, then (tanh+1)/2 or sigmoid.
+ * y NHWC bf16 [B][H][W][Cp] -> img NCHW fp32 [B][3][H][W]. */
+int onr_head_fwd(const void* y_bf16, int B, int H, int W, int C, int Cp,
+                 const float* Wh /*[3,C]*/, const float* bh /*[3]*/, int use_sigmoid,
+                 float* img, void* stream);
+/* Backward: gimg NCHW fp32, img (saved output) -> gWh,gbh (+=) and
+ * dz[B][H][W][Cp] bf16 = (Wh^T g_pre) * dsilu  (dsilu = SiLU' of the last block, same layout). */
+int onr_head_bwd(const float* gimg, const float* img, const void* y_bf16, const void* dsilu_bf16,
+                 int B, int H, int W, int C, int Cp, const float* Wh, int use_sigmoid,
+                 float* gWh, float* gbh, void* dz_bf16, void* stream);
+
+/* ------------------------------------------------------------------ A7+A10: Fusion6 loss, PSNR, MS-SSIM
+ * utils.py:159-160 with pytorch_msssim 0.2.1 ssim (11-tap sigma 1.5 valid windows, C1=1e-4, C2=9e-4),
+ * utils.py:191-199 (psnr_fn).  pred/target NCHW fp32 [B][3][H][W].
+ * out[0]=loss, out[1]=L1 mean, out[2]=SSIM mean, out[3]=MSE, out[4]=PSNR (over the whole batch).
+ * grad_pred (may be NULL) receives dloss/dpred * grad_scale.  work: onr_loss_workspace_bytes(). */
+size_t onr_loss_workspace_bytes(int B, int H, int W);
+int onr_fusion6_fwd_bwd(const float* pred, const float* target, int B, int H, int W,
+                        float w_l1, float w_ssim, float grad_scale,
+                        float* out5, float* grad_pred, void* work, void* stream);
+/* utils.py:201-211 / pytorch_msssim.ms_ssim: 5 scales, avg_pool2d(2, padding = dim%2). out[1]. */
+size_t onr_msssim_workspace_bytes(int B, int H, int W);
+int onr_msssim(const float* pred, const float* target, int B, int H, int W, float* out1,
+               void* work, void* stream);
+
+/* ------------------------------------------------------------------ A9: fused multi-tensor Adam
+ * torch.optim.Adam as used at main_train.py:196, :248-250 (betas (beta,0.999), eps 1e-8, no wd).
+ * table: n_tensors entries {param, grad, m, v, numel} as 5 x uint64 each (device array).
+ * lr_dev, step_dev: device scalars (lr from adjust_lr, utils.py:240-259; step count t >= 1).
+ * grad_scale multiplies grads (1/world_size); grads are zeroed after use when zero_grad != 0. */
+int onr_adam_multi(const uint64_t* table, int n_tensors, size_t total_numel,
+                   const float* lr_dev, const int* step_dev, float beta1, float beta2, float eps,
+                   float grad_scale, int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------ A12/A13: eval-side weight transforms
+ * main_eval.py:572-587 (global L1 magnitude prune): count of |w| <= thr over a list of tensors. */
+int onr_abs_count_le(const float* w, size_t n, float thr, unsigned long long* count, void* stream);
+int onr_apply_magnitude_mask(float* w, size_t n, float thr, void* stream);
+/* utils.py:11-67 quantize_per_tensor with axis 0 over rows of a [rows, cols] view (axis -1: rows=1):
+ * min/max over non-zero entries, scale=(max-min)/2^bit, q=round((t-min)/(scale+1e-19)),
+ * new=min+scale*q.  q_out and new_out may alias nothing; either may be NULL. */
+int onr_quant_rows(const float* t, int rows, size_t cols, int bit, float* q_out, float* new_out,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OREPNERV_H */
