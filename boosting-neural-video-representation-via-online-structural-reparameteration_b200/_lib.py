@@ -1,0 +1,147 @@
+"""ctypes binding of liborepnerv.so (the C ABI declared in include/orepnerv.h).
+
+There is exactly one compute path: the sm_100a kernels in that library.  If the library is missing,
+cannot be loaded, or the current device is not a B200-class GPU, the callers raise — nothing here (or
+anywhere in the package) falls back to PyTorch ops or to the CPU oracle.
+"""
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liborepnerv.so")
+HEADER_PATH = os.path.join(HERE, "..", "include", "orepnerv.h")
+
+_lib = None
+_device_checked = False
+
+vp = C.c_void_p
+i32 = C.c_int
+f32 = C.c_float
+sz = C.c_size_t
+u32 = C.c_uint32
+
+
+class ConvDesc(C.Structure):
+    """onr_conv_desc"""
+    _fields_ = [
+        ("kind", i32), ("B", i32), ("H", i32), ("W", i32),
+        ("a", vp), ("a_cp", i32), ("a_s", i32),
+        ("w", vp), ("n_rows", i32),
+        ("n_total", i32),
+        ("out", vp), ("out_cp", i32), ("out_s", i32),
+        ("out_d", vp),
+        ("bias_p", vp),
+        ("dmul", vp),
+    ]
+
+
+class WgradDesc(C.Structure):
+    """onr_wgrad_desc"""
+    _fields_ = [
+        ("B", i32), ("H", i32), ("W", i32),
+        ("x", vp), ("x_cp", i32),
+        ("dz", vp), ("dz_cp", i32), ("s", i32),
+        ("dKp", vp),
+        ("dbias_p", vp),
+    ]
+
+
+CONV_FPROP_TRAIN, CONV_FPROP_INFER, CONV_DGRAD = 0, 1, 2
+
+_SIGNATURES = {
+    "onr_abi_version": (i32, []),
+    "onr_last_error": (C.c_char_p, []),
+    "onr_check_device": (i32, []),
+    "onr_launch_count": (C.c_ulonglong, []),
+    "onr_pe_stem_fwd": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "onr_pos_encoding": (i32, [vp, i32, vp, i32, vp, vp]),
+    "onr_frame_u8_to_f32": (i32, [vp, sz, vp, vp]),
+    "onr_stem_bwd": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "onr_erb_fold_fwd": (i32, [vp] * 9 + [i32, i32, vp, vp, vp, vp]),
+    "onr_erb_fold_bwd": (i32, [vp] * 6 + [i32, i32] + [vp] * 10 + [vp]),
+    "onr_pack_weights": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "onr_unpack_wgrad": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+    "onr_conv_plan_create": (i32, [C.POINTER(vp), C.POINTER(ConvDesc)]),
+    "onr_conv_plan_run": (i32, [vp, vp]),
+    "onr_conv_plan_destroy": (None, [vp]),
+    "onr_conv_tile_n": (i32, [i32, C.POINTER(i32), C.POINTER(i32)]),
+    "onr_wgrad_plan_create": (i32, [C.POINTER(vp), C.POINTER(WgradDesc)]),
+    "onr_wgrad_plan_run": (i32, [vp, vp]),
+    "onr_wgrad_plan_destroy": (None, [vp]),
+    "onr_simt_conv": (i32, [C.POINTER(ConvDesc), vp]),
+    "onr_simt_wgrad": (i32, [C.POINTER(WgradDesc), vp]),
+    "onr_nchw_to_nhwc_bf16": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
+    "onr_nhwc_bf16_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
+    "onr_head_fwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
+    "onr_head_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp]),
+    "onr_loss_workspace_bytes": (sz, [i32, i32, i32]),
+    "onr_fusion6_fwd_bwd": (i32, [vp, vp, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp]),
+    "onr_msssim_workspace_bytes": (sz, [i32, i32, i32]),
+    "onr_msssim": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+    "onr_adam_multi": (i32, [vp, i32, sz, vp, vp, f32, f32, f32, f32, i32, vp]),
+    "onr_sched_tick": (i32, [vp, vp, C.c_double, i32, i32, i32, i32, i32, vp]),
+    "onr_abs_radix_hist": (i32, [vp, sz, u32, u32, i32, vp, vp]),
+    "onr_apply_magnitude_mask": (i32, [vp, sz, f32, vp, vp, vp]),
+    "onr_quant_rows": (i32, [vp, i32, sz, i32, vp, vp, vp, vp]),
+}
+
+
+def declared_symbols():
+    """Every function name include/orepnerv.h declares (used by the CPU test that checks exports)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(onr_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """Load the shared library (no GPU needed) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.onr_abi_version() != 1:
+        raise RuntimeError("liborepnerv.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().onr_last_error().decode(errors="replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"liborepnerv {what} failed (rc={rc}): {last_error()}")
+
+
+def lib():
+    """Library handle for compute calls: also verifies once that the current device is sm_100."""
+    global _device_checked
+    l = load()
+    if not _device_checked:
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("orepnerv needs a CUDA device (B200, sm_100a); there is no CPU path")
+        check(l.onr_check_device(), "onr_check_device")
+        _device_checked = True
+    return l
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -16,6 +16,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -74,6 +77,8 @@ extern "C" {
 int onr_abi_version(void) { return ONR_ABI_VERSION; }
 
 const char* onr_last_error(void) { return onr::g_err; }
+
+unsigned long long onr_launch_count(void) { return __atomic_load_n(&onr::g_launches, __ATOMIC_RELAXED); }
 
 int onr_check_device(void) {
     int dev = 0;

@@ -13,6 +13,7 @@
 namespace onr {
 
 void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of the library bumps a process-wide counter (onr_launch_count)
 
 #define ONR_REQUIRE(cond, ...)                \
     do {                                      \
@@ -40,6 +41,7 @@ void set_error(const char* fmt, ...);
                              __FILE__, __LINE__);                                        \
             return static_cast<int>(_e);                                                 \
         }                                                                                \
+        ::onr::count_launch();                                                           \
     } while (0)
 
 inline int num_sms() {

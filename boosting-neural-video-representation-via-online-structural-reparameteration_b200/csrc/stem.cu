@@ -1,0 +1,209 @@
+// stem.cu — frame-index positional encoding + the two-layer stem MLP, forward and backward.
+//
+// Forward (reference utils.py:121-129 PositionalEncoding.forward; model.py:174-188 MLP;
+// model.py:612-613 stem + view):
+//   e[b,2i] = sin((t_b * f_i) * pi), e[b,2i+1] = cos(...)   with f_i = fp32(lbase**i) from the host
+//   h1 = SiLU(W1 e + b1);  o = SiLU(W2 h1 + b2);  x0[b,h,w,c] = o[b, c*fh*fw + h*fw + w]  (NHWC bf16)
+// Backward: rank-1 gW2, W2^T g for dh1, then the 80x512 layer.
+// W2 (7.7 MB at fc 9_16_26, 33 MB at 9_16_112) is read exactly once per pass with 128-bit loads.
+#include "onr_common.cuh"
+
+namespace onr {
+
+__global__ void pe_layer1_kernel(const float* __restrict__ t_norm, const float* __restrict__ freqs, int levels,
+                                 const float* __restrict__ W1, const float* __restrict__ b1, int hid,
+                                 float* __restrict__ embed, float* __restrict__ pre1, float* __restrict__ h1) {
+    extern __shared__ float se[];  // [2*levels]
+    const int b = blockIdx.x;
+    const int E = 2 * levels;
+    if (t_norm != nullptr) {
+        const float t = t_norm[b];
+        const float pi = 3.14159265358979323846f;
+        for (int i = threadIdx.x; i < levels; i += blockDim.x) {
+            const float v = __fmul_rn(__fmul_rn(t, freqs[i]), pi);   // same rounding order as the reference
+            const float s = sinf(v), c = cosf(v);
+            se[2 * i] = s;
+            se[2 * i + 1] = c;
+            embed[(size_t)b * E + 2 * i] = s;
+            embed[(size_t)b * E + 2 * i + 1] = c;
+        }
+    } else {
+        // the caller already holds the embedding (Generator.forward(embed) of the reference API)
+        for (int i = threadIdx.x; i < E; i += blockDim.x) se[i] = embed[(size_t)b * E + i];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+        const float* w = W1 + (size_t)j * E;
+        float acc = 0.0f;
+        for (int e = 0; e < E; ++e) acc = fmaf(w[e], se[e], acc);
+        acc += b1[j];
+        pre1[(size_t)b * hid + j] = acc;
+        h1[(size_t)b * hid + j] = acc / (1.0f + expf(-acc));
+    }
+}
+
+__global__ void pos_encoding_kernel(const float* __restrict__ t_norm, int B, const float* __restrict__ freqs,
+                                    int levels, float* __restrict__ embed) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * levels) return;
+    const int b = idx / levels, i = idx % levels;
+    const float v = __fmul_rn(__fmul_rn(t_norm[b], freqs[i]), 3.14159265358979323846f);
+    embed[(size_t)b * 2 * levels + 2 * i] = sinf(v);
+    embed[(size_t)b * 2 * levels + 2 * i + 1] = cosf(v);
+}
+
+// one warp per output position p = (h*fw + w)*Cp + c of the NHWC stem output
+__global__ void stem_layer2_kernel(const float* __restrict__ h1, int B, int hid, const float* __restrict__ W2,
+                                   const float* __restrict__ b2, int fc_dim, int fh, int fw, int Cp,
+                                   __nv_bfloat16* __restrict__ x0, __nv_bfloat16* __restrict__ dstem) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int total = fh * fw * Cp;
+    for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < total; p += gridDim.x * warps_per_block) {
+        const int c = p % Cp;
+        const int hw = p / Cp;
+        if (c >= fc_dim) {
+            if (lane == 0)
+                for (int b = 0; b < B; ++b) {
+                    x0[(size_t)b * total + p] = __float2bfloat16(0.0f);
+                    dstem[(size_t)b * total + p] = __float2bfloat16(0.0f);
+                }
+            continue;
+        }
+        const int o = c * fh * fw + hw;
+        const float4* wrow = reinterpret_cast<const float4*>(W2 + (size_t)o * hid);
+        for (int b = 0; b < B; ++b) {
+            const float4* hv = reinterpret_cast<const float4*>(h1 + (size_t)b * hid);
+            float acc = 0.0f;
+            for (int j = lane; j < hid / 4; j += 32) {
+                const float4 w = __ldg(wrow + j), h = hv[j];
+                acc = fmaf(w.x, h.x, acc);
+                acc = fmaf(w.y, h.y, acc);
+                acc = fmaf(w.z, h.z, acc);
+                acc = fmaf(w.w, h.w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                const float z = acc + b2[o];
+                const float sg = 1.0f / (1.0f + expf(-z));
+                const float y = z * sg;
+                x0[(size_t)b * total + p] = __float2bfloat16(y);
+                dstem[(size_t)b * total + p] = __float2bfloat16(sg + y * (1.0f - sg));
+            }
+        }
+    }
+}
+
+// Each block owns a chunk of output rows o; thread t owns hidden units j = t, t+blockDim, ...
+// gW2[o,j] += g*h1[j];  gb2[o] += g;  dh1[b,j] += W2[o,j]*g  (block-partial, then atomics).
+constexpr int kStemRows = 16;
+constexpr int kStemMaxJ = 8;
+__global__ void stem_bwd_layer2_kernel(const __nv_bfloat16* __restrict__ g0, int B, const float* __restrict__ h1,
+                                       int hid, const float* __restrict__ W2, int fc_dim, int fh, int fw, int Cp,
+                                       float* __restrict__ gW2, float* __restrict__ gb2,
+                                       float* __restrict__ dh1) {
+    const int b = blockIdx.y;
+    const int n_out = fc_dim * fh * fw;
+    const int o_begin = blockIdx.x * kStemRows;
+    const int o_end = min(n_out, o_begin + kStemRows);
+    float hreg[kStemMaxJ], acc[kStemMaxJ];
+#pragma unroll
+    for (int u = 0; u < kStemMaxJ; ++u) {
+        const int j = threadIdx.x + u * blockDim.x;
+        hreg[u] = j < hid ? h1[(size_t)b * hid + j] : 0.0f;
+        acc[u] = 0.0f;
+    }
+    for (int o = o_begin; o < o_end; ++o) {
+        const int c = o / (fh * fw), hw = o % (fh * fw);
+        const float g = __bfloat162float(g0[((size_t)b * fh * fw + hw) * Cp + c]);
+        if (threadIdx.x == 0) atomicAdd(&gb2[o], g);
+#pragma unroll
+        for (int u = 0; u < kStemMaxJ; ++u) {
+            const int j = threadIdx.x + u * blockDim.x;
+            if (j < hid) {
+                const size_t idx = (size_t)o * hid + j;
+                acc[u] = fmaf(__ldg(W2 + idx), g, acc[u]);
+                if (B == 1) gW2[idx] += g * hreg[u];
+                else atomicAdd(&gW2[idx], g * hreg[u]);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kStemMaxJ; ++u) {
+        const int j = threadIdx.x + u * blockDim.x;
+        if (j < hid) atomicAdd(&dh1[(size_t)b * hid + j], acc[u]);
+    }
+}
+
+__global__ void stem_bwd_layer1_kernel(const float* __restrict__ dh1, const float* __restrict__ pre1,
+                                       const float* __restrict__ embed, int B, int hid, int E,
+                                       float* __restrict__ gW1, float* __restrict__ gb1) {
+    // one thread per (j, e) pair plus bias; sums over the batch
+    const int total = hid * E;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx / E, e = idx % E;
+        float gw = 0.0f, gb = 0.0f;
+        for (int b = 0; b < B; ++b) {
+            const float z = pre1[(size_t)b * hid + j];
+            const float sg = 1.0f / (1.0f + expf(-z));
+            const float dpre = dh1[(size_t)b * hid + j] * (sg + z * sg * (1.0f - sg));
+            gw = fmaf(dpre, embed[(size_t)b * E + e], gw);
+            gb += dpre;
+        }
+        gW1[idx] += gw;
+        if (e == 0) gb1[j] += gb;
+    }
+}
+
+}  // namespace onr
+
+extern "C" {
+
+int onr_pe_stem_fwd(const float* t_norm, int B, const float* freqs, int levels, const float* W1,
+                    const float* b1, int hid, const float* W2, const float* b2, int fc_dim, int fh, int fw,
+                    int Cp, float* embed, float* pre1, float* h1, void* x0, void* dstem, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(B >= 1 && levels >= 1 && hid % 4 == 0 && Cp % 32 == 0 && Cp >= fc_dim, "stem: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    pe_layer1_kernel<<<B, 256, 2 * levels * sizeof(float), st>>>(t_norm, freqs, levels, W1, b1, hid, embed,
+                                                                 pre1, h1);
+    ONR_LAUNCH_CHECK();
+    const int total = fh * fw * Cp;
+    const int wpb = 8;
+    int grid = ceil_div(total, wpb);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    stem_layer2_kernel<<<grid, wpb * 32, 0, st>>>(h1, B, hid, W2, b2, fc_dim, fh, fw, Cp,
+                                                  reinterpret_cast<__nv_bfloat16*>(x0),
+                                                  reinterpret_cast<__nv_bfloat16*>(dstem));
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
+
+int onr_pos_encoding(const float* t_norm, int B, const float* freqs, int levels, float* embed, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(B >= 1 && levels >= 1, "pos_encoding: bad shape");
+    pos_encoding_kernel<<<ceil_div(B * levels, 128), 128, 0, (cudaStream_t)stream>>>(t_norm, B, freqs, levels,
+                                                                                    embed);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
+
+int onr_stem_bwd(const void* g0, int B, const float* embed, int emb_len, const float* pre1, const float* h1,
+                 int hid, const float* W2, int fc_dim, int fh, int fw, int Cp, float* gW1, float* gb1,
+                 float* gW2, float* gb2, float* scratch_dh1, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(hid <= 128 * kStemMaxJ, "stem: hidden width %d too large", hid);
+    cudaStream_t st = (cudaStream_t)stream;
+    ONR_CUDA(cudaMemsetAsync(scratch_dh1, 0, (size_t)B * hid * sizeof(float), st));
+    const int n_out = fc_dim * fh * fw;
+    dim3 grid(ceil_div(n_out, kStemRows), B);
+    stem_bwd_layer2_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g0), B, h1, hid, W2,
+                                                 fc_dim, fh, fw, Cp, gW2, gb2, scratch_dh1);
+    ONR_LAUNCH_CHECK();
+    stem_bwd_layer1_kernel<<<ceil_div(hid * emb_len, 256), 256, 0, st>>>(scratch_dh1, pre1, embed, B, hid,
+                                                                        emb_len, gW1, gb1);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+"""Device-side executor of the frame-fitting hot path.
+
+One `NetExecutor` owns, for a `Generator` at a fixed batch size, every persistent HBM buffer (NHWC bf16
+activations, SiLU' maps, dZ maps, folded kernels and their packed bf16 operand copies, gradient
+staging) and the TMA-descriptor plans of the tcgen05 convolution kernels, and sequences the kernels of
+liborepnerv.so for
+
+    forward  : PE + stem -> per block [ERB fold -> pack -> conv3x3+PixelShuffle+SiLU] -> RGB head
+    backward : head -> per block [wgrad, dgrad (x SiLU'), unpack, fold backward] -> stem
+
+which is reference main_train.py:238 (`model(embed_input)`) and :249 (`loss_sum.backward()`) for
+model.py:611-625 / :518-567.  PyTorch only provides the allocations and the stream.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, WgradDesc, check, ptr
+
+
+def pad32(c):
+    return (c + 31) // 32 * 32
+
+
+def conv_tile_n(n_total):
+    bn, nt = C.c_int(0), C.c_int(0)
+    check(_lib.load().onr_conv_tile_n(n_total, C.byref(bn), C.byref(nt)), "onr_conv_tile_n")
+    return bn.value, nt.value
+
+
+class BlockGeom:
+    """Shapes of one NeRVBlock (reference model.py:303-343) in the padded NHWC / implicit-GEMM world."""
+
+    def __init__(self, cin, cnew, s, h, w):
+        self.cin, self.cnew, self.s, self.h, self.w = cin, cnew, s, h, w
+        self.cout = cnew * s * s                 # reference conv output channels (PixelShuffle order)
+        self.cpi, self.cpo = pad32(cin), pad32(cnew)
+        self.nk = s * s * self.cpo               # GEMM N of fprop / K of dgrad, n' = (i*s+j)*Cpo + c
+        bn, nt = conv_tile_n(self.nk)
+        self.npad = bn * nt                      # rows of the packed fprop weights
+        bn2, nt2 = conv_tile_n(self.cpi)
+        self.cpi_rows = bn2 * nt2                # rows of the packed dgrad weights
+        self.ho, self.wo = h * s, w * s
+
+
+class _Plan:
+    """RAII wrapper around onr_conv_plan / onr_wgrad_plan handles."""
+
+    def __init__(self, handle, destroy):
+        self.handle, self._destroy = handle, destroy
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _conv_plan(lib, **kw):
+    d = ConvDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    h = C.c_void_p()
+    check(lib.onr_conv_plan_create(C.byref(h), C.byref(d)), "onr_conv_plan_create")
+    return _Plan(h, lib.onr_conv_plan_destroy)
+
+
+def _wgrad_plan(lib, **kw):
+    d = WgradDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    h = C.c_void_p()
+    check(lib.onr_wgrad_plan_create(C.byref(h), C.byref(d)), "onr_wgrad_plan_create")
+    return _Plan(h, lib.onr_wgrad_plan_destroy)
+
+
+class NetExecutor:
+    def __init__(self, gen, batch, train):
+        self.lib = _lib.lib()
+        self.gen, self.B, self.train = gen, batch, train
+        dev = next(gen.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("orepnerv Generator must live on a CUDA (sm_100a) device; no CPU path exists")
+        self.dev = dev
+        B = batch
+        bf16, f32 = torch.bfloat16, torch.float32
+
+        def zeros(*shape, dtype=f32):
+            return torch.zeros(*shape, dtype=dtype, device=dev)
+
+        # ---- geometry -------------------------------------------------------------------------
+        self.geoms = []
+        h, w, c = gen.fc_h, gen.fc_w, gen.fc_dim
+        for blk in gen.layers:
+            g = BlockGeom(blk.ngf, blk.new_ngf, blk.stride, h, w)
+            assert g.cin == c
+            self.geoms.append(g)
+            h, w, c = g.ho, g.wo, g.cnew
+        self.H, self.W, self.C_last = h, w, c
+        L = len(self.geoms)
+        self.L = L
+
+        # ---- stem ------------------------------------------------------------------------------
+        lin1, lin2 = gen.stem[0], gen.stem[2]
+        self.E, self.hid = lin1.in_features, lin1.out_features
+        self.embed = zeros(B, self.E)
+        self.pre1, self.h1, self.dh1 = zeros(B, self.hid), zeros(B, self.hid), zeros(B, self.hid)
+
+        # ---- activations: x[l] is the input of block l (x[L] = last block output) ----------------
+        self.x, self.d, self.dz = [], [], []
+        for l in range(L + 1):
+            if l == 0:
+                hh, ww, cp = gen.fc_h, gen.fc_w, self.geoms[0].cpi
+            else:
+                g = self.geoms[l - 1]
+                hh, ww, cp = g.ho, g.wo, g.cpo
+            self.x.append(zeros(B, hh, ww, cp, dtype=bf16))
+            # x[0]/d[0] come from the stem kernel which always writes both
+            self.d.append(zeros(B, hh, ww, cp, dtype=bf16) if (train or l == 0) else None)
+            self.dz.append(zeros(B, hh, ww, cp, dtype=bf16) if train else None)
+        self.img = zeros(B, 3, self.H, self.W)
+
+        # ---- per block weights / gradient staging ------------------------------------------------
+        self.K, self.bias, self.T, self.wf, self.wd, self.bias_p = [], [], [], [], [], []
+        self.dKp, self.dbias_p, self.dK, self.dbias, self.dT = [], [], [], [], []
+        for g, blk in zip(self.geoms, gen.layers):
+            erb = blk.is_erb_train()
+            self.K.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
+            self.bias.append(zeros(g.cout) if erb else None)
+            self.T.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
+            self.wf.append(zeros(9, g.npad, g.cpi, dtype=bf16))
+            self.wd.append(zeros(9, g.cpi_rows, g.nk, dtype=bf16) if train else None)
+            self.bias_p.append(zeros(g.npad))
+            if train:
+                self.dKp.append(zeros(g.nk, 9, g.cpi))
+                self.dbias_p.append(zeros(g.nk))
+                self.dK.append(zeros(g.cout, g.cin, 3, 3))
+                self.dbias.append(zeros(g.cout))
+                self.dT.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
+            else:
+                for lst in (self.dKp, self.dbias_p, self.dK, self.dbias, self.dT):
+                    lst.append(None)
+
+        # ---- plans -----------------------------------------------------------------------------
+        lib = self.lib
+        self.fprop, self.dgrad, self.wgrad = [], [], []
+        for l, g in enumerate(self.geoms):
+            self.fprop.append(_conv_plan(
+                lib, kind=_lib.CONV_FPROP_TRAIN if train else _lib.CONV_FPROP_INFER,
+                B=B, H=g.h, W=g.w, a=ptr(self.x[l]), a_cp=g.cpi, a_s=1,
+                w=ptr(self.wf[l]), n_rows=g.npad, n_total=g.nk,
+                out=ptr(self.x[l + 1]), out_cp=g.cpo, out_s=g.s,
+                out_d=ptr(self.d[l + 1]) if train else None, bias_p=ptr(self.bias_p[l]), dmul=None))
+            if train:
+                self.dgrad.append(_conv_plan(
+                    lib, kind=_lib.CONV_DGRAD, B=B, H=g.h, W=g.w,
+                    a=ptr(self.dz[l + 1]), a_cp=g.cpo, a_s=g.s,
+                    w=ptr(self.wd[l]), n_rows=g.cpi_rows, n_total=g.cpi,
+                    out=ptr(self.dz[l]), out_cp=g.cpi, out_s=1, out_d=None, bias_p=None,
+                    dmul=ptr(self.d[l])))
+                self.wgrad.append(_wgrad_plan(
+                    lib, B=B, H=g.h, W=g.w, x=ptr(self.x[l]), x_cp=g.cpi,
+                    dz=ptr(self.dz[l + 1]), dz_cp=g.cpo, s=g.s,
+                    dKp=ptr(self.dKp[l]), dbias_p=ptr(self.dbias_p[l])))
+        self._zero_list = [t for t in self.dKp + self.dbias_p if t is not None]
+
+    # ------------------------------------------------------------------------------------- helpers
+    def _block_kernel(self, l):
+        """(K, bias) fp32 OIHW of block l, folding the ERB branches on the device when needed."""
+        blk = self.gen.layers[l]
+        g = self.geoms[l]
+        st = _lib.stream()
+        if blk.is_erb_train():
+            b = blk
+            check(self.lib.onr_erb_fold_fwd(
+                ptr(b.rbr_3x3_branch.weight), ptr(b.rbr_3x3_branch.bias),
+                ptr(b.rbr_1x3_branch.weight), ptr(b.rbr_1x3_branch.bias),
+                ptr(b.rbr_3x1_branch.weight), ptr(b.rbr_3x1_branch.bias),
+                ptr(b.rbr_1x1_3x3_1x1_branch_1x1_1.weight), ptr(b.rbr_1x1_3x3_1x1_branch_3x3.weight),
+                ptr(b.rbr_1x1_3x3_1x1_branch_1x1_2.weight),
+                g.cin, g.cout, ptr(self.K[l]), ptr(self.bias[l]), ptr(self.T[l]), st), "onr_erb_fold_fwd")
+            return self.K[l], self.bias[l]
+        conv = blk.single_conv()
+        return conv.weight.detach(), conv.bias.detach()
+
+    def refresh_weights(self):
+        """Fold (ERB) and pack every block kernel into the bf16 operand layouts."""
+        st = _lib.stream()
+        for l, g in enumerate(self.geoms):
+            K, b = self._block_kernel(l)
+            check(self.lib.onr_pack_weights(
+                ptr(K), ptr(b), g.cin, g.cnew, g.s, g.npad, g.cpi_rows,
+                ptr(self.wf[l]), ptr(self.wd[l]) if self.train else None, ptr(self.bias_p[l]), st),
+                "onr_pack_weights")
+
+    # ------------------------------------------------------------------------------------- forward
+    def forward(self, embed=None, t_norm=None, freqs=None, refresh=True):
+        """Runs the decoder; returns the image buffer [B,3,H,W] fp32 (owned by the executor).
+        Either `embed` [B,2L] (reference entry) or `t_norm` [B] + `freqs` [L] (fused PE) is given."""
+        gen, st = self.gen, _lib.stream()
+        lin1, lin2 = gen.stem[0], gen.stem[2]
+        g0 = self.geoms[0]
+        if t_norm is None:
+            if embed is None:
+                raise ValueError("forward needs embed or t_norm")
+            self.embed.copy_(embed.reshape(self.B, self.E))
+        elif freqs is None:
+            raise ValueError("t_norm needs the frequency table of the PositionalEncoding")
+        check(self.lib.onr_pe_stem_fwd(
+            ptr(t_norm), self.B, ptr(freqs), self.E // 2,
+            ptr(lin1.weight), ptr(lin1.bias), self.hid, ptr(lin2.weight), ptr(lin2.bias),
+            gen.fc_dim, gen.fc_h, gen.fc_w, g0.cpi,
+            ptr(self.embed), ptr(self.pre1), ptr(self.h1), ptr(self.x[0]), ptr(self.d[0]), st),
+            "onr_pe_stem_fwd")
+        if refresh:
+            self.refresh_weights()
+        for l in range(self.L):
+            check(self.lib.onr_conv_plan_run(self.fprop[l].handle, st), "onr_conv_plan_run(fprop)")
+        head = gen.head_conv()
+        check(self.lib.onr_head_fwd(
+            ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, self.geoms[-1].cpo,
+            ptr(head.weight), ptr(head.bias), 1 if gen.sigmoid else 0, ptr(self.img), st), "onr_head_fwd")
+        return self.img
+
+    # ------------------------------------------------------------------------------------ backward
+    def backward(self, gimg, grads):
+        """Backward of `forward`. `grads` maps parameter name -> fp32 gradient tensor; every tensor must be
+        zero on entry (the kernels accumulate into the ERB branch / stem / head gradients and overwrite the
+        single-branch conv gradients)."""
+        assert self.train
+        gen, st, lib = self.gen, _lib.stream(), self.lib
+        for t in self._zero_list:
+            t.zero_()
+        head = gen.head_conv()
+        hname = gen.head_name()
+        gL = self.geoms[-1]
+        check(lib.onr_head_bwd(
+            ptr(gimg), ptr(self.img), ptr(self.x[self.L]), ptr(self.d[self.L]), self.B, self.H, self.W,
+            self.C_last, gL.cpo, ptr(head.weight), 1 if gen.sigmoid else 0,
+            ptr(grads[hname + ".weight"]), ptr(grads[hname + ".bias"]), ptr(self.dz[self.L]), st), "onr_head_bwd")
+        for l in reversed(range(self.L)):
+            g, blk = self.geoms[l], gen.layers[l]
+            check(lib.onr_wgrad_plan_run(self.wgrad[l].handle, st), "onr_wgrad_plan_run")
+            check(lib.onr_conv_plan_run(self.dgrad[l].handle, st), "onr_conv_plan_run(dgrad)")
+            if blk.is_erb_train():
+                dK, db = self.dK[l], self.dbias[l]
+            else:   # single-branch block: dK is the parameter gradient itself (grads are zero on entry)
+                name = f"layers.{l}." + blk.single_conv_name()
+                dK, db = grads[name + ".weight"], grads[name + ".bias"]
+            check(lib.onr_unpack_wgrad(ptr(self.dKp[l]), ptr(self.dbias_p[l]), g.cin, g.cnew, g.s,
+                                       ptr(dK), ptr(db), st), "onr_unpack_wgrad")
+            if blk.is_erb_train():
+                self.scatter_block_grads(l, grads)
+        lin1 = gen.stem[0]
+        lin2 = gen.stem[2]
+        g0 = self.geoms[0]
+        check(lib.onr_stem_bwd(
+            ptr(self.dz[0]), self.B, ptr(self.embed), self.E, ptr(self.pre1), ptr(self.h1), self.hid,
+            ptr(lin2.weight), gen.fc_dim, gen.fc_h, gen.fc_w, g0.cpi,
+            ptr(grads["stem.0.weight"]), ptr(grads["stem.0.bias"]),
+            ptr(grads["stem.2.weight"]), ptr(grads["stem.2.bias"]), ptr(self.dh1), st), "onr_stem_bwd")
+
+    def scatter_block_grads(self, l, grads):
+        """dK/dbias of ERB block l -> gradients of its nine branch tensors (fold backward)."""
+        g, blk, st = self.geoms[l], self.gen.layers[l], _lib.stream()
+        pfx = f"layers.{l}."
+        if True:
+            b = blk
+            check(self.lib.onr_erb_fold_bwd(
+                ptr(self.dK[l]), ptr(self.dbias[l]),
+                ptr(b.rbr_1x1_3x3_1x1_branch_1x1_1.weight), ptr(b.rbr_1x1_3x3_1x1_branch_3x3.weight),
+                ptr(b.rbr_1x1_3x3_1x1_branch_1x1_2.weight), ptr(self.T[l]), g.cin, g.cout,
+                ptr(grads[pfx + "rbr_3x3_branch.weight"]), ptr(grads[pfx + "rbr_3x3_branch.bias"]),
+                ptr(grads[pfx + "rbr_1x3_branch.weight"]), ptr(grads[pfx + "rbr_1x3_branch.bias"]),
+                ptr(grads[pfx + "rbr_3x1_branch.weight"]), ptr(grads[pfx + "rbr_3x1_branch.bias"]),
+                ptr(grads[pfx + "rbr_1x1_3x3_1x1_branch_1x1_1.weight"]),
+                ptr(grads[pfx + "rbr_1x1_3x3_1x1_branch_3x3.weight"]),
+                ptr(grads[pfx + "rbr_1x1_3x3_1x1_branch_1x1_2.weight"]),
+                ptr(self.dT[l]), st), "onr_erb_fold_bwd")

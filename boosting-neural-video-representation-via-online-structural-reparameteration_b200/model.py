@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference `model.py` for the frame-fitting hot path.
+
+Same public surface (reference model.py:303-625): `Generator(**kargs)`, `NeRVBlock(**kargs)` with
+`get_equivalent_kernel_bias()` / `switch_to_deploy()`, identical sub-module names, construction order
+(so `torch.manual_seed(s)` yields bit-identical initial parameters) and `state_dict()` keys/shapes/dtypes
+(so reference checkpoints load here and ours load there).  What differs is below the surface: no
+`F.conv2d`, `nn.PixelShuffle`, `nn.SiLU`, `nn.Linear` kernel is ever dispatched — the modules are
+parameter containers and every arithmetic step runs in liborepnerv.so (sm_100a) via `engine.NetExecutor`.
+
+Scope: branch_type in {NeRV_vanilla, ERB}, act 'swish', norm 'none',
+num_blocks 1, single-resolution head.  Anything else raises NotImplementedError — there is no fallback.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, ptr
+from .engine import NetExecutor, pad32, conv_tile_n, _conv_plan, _wgrad_plan
+
+SUPPORTED_BRANCHES = ("NeRV_vanilla", "ERB")
+_ERB_BRANCHES = ("rbr_3x3_branch", "rbr_3x1_branch", "rbr_1x3_branch", "rbr_1x1_3x3_1x1_branch_1x1_1",
+                 "rbr_1x1_3x3_1x1_branch_3x3", "rbr_1x1_3x3_1x1_branch_1x1_2")
+
+
+def _require(cond, what):
+    if not cond:
+        raise NotImplementedError(
+            f"{what} is outside the B200 hot path (supported: branch_type NeRV_vanilla|ERB, act swish, "
+            "norm none, num_blocks 1, single_res); no fallback path exists")
+
+
+def _fire_prune_hooks(conv):
+    """torch.nn.utils.prune recomputes `.weight = weight_orig * weight_mask` in a forward-pre-hook of the
+    conv module (reference main_eval.py:572-587 relies on that).  We never call the module, so run the
+    hooks by hand before reading `.weight`."""
+    for hook in conv._forward_pre_hooks.values():
+        hook(conv, None)
+
+
+class _FoldFunction(torch.autograd.Function):
+    """ERB online fold (reference model.py:450-516) with its analytic backward."""
+
+    @staticmethod
+    def forward(ctx, w3x3, b3x3, w1x3, b1x3, w3x1, b3x1, w1, w2, w3):
+        lib = _lib.lib()
+        cout, cin = w3x3.shape[0], w3x3.shape[1]
+        args = [t.detach().contiguous() for t in (w3x3, b3x3, w1x3, b1x3, w3x1, b3x1, w1, w2, w3)]
+        K = torch.empty_like(args[0])
+        bias = torch.empty_like(args[1])
+        T = torch.empty_like(args[0])
+        check(lib.onr_erb_fold_fwd(*[ptr(t) for t in args], cin, cout, ptr(K), ptr(bias), ptr(T),
+                                   _lib.stream()), "onr_erb_fold_fwd")
+        ctx.save_for_backward(args[6], args[7], args[8], T)
+        ctx.shapes = [t.shape for t in args]
+        return K, bias
+
+    @staticmethod
+    def backward(ctx, dK, dbias):
+        lib = _lib.lib()
+        w1, w2, w3, T = ctx.saved_tensors
+        cout, cin = T.shape[0], T.shape[1]
+        dK = dK.contiguous()
+        dbias = dbias.contiguous() if dbias is not None else torch.zeros(cout, device=dK.device)
+        grads = [torch.zeros(s, dtype=torch.float32, device=dK.device) for s in ctx.shapes]
+        dT = torch.empty_like(T)
+        g3, gb3, g13, gb13, g31, gb31, gw1, gw2, gw3 = grads
+        check(lib.onr_erb_fold_bwd(ptr(dK), ptr(dbias), ptr(w1), ptr(w2), ptr(w3), ptr(T), cin, cout,
+                                   ptr(g3), ptr(gb3), ptr(g13), ptr(gb13), ptr(g31), ptr(gb31),
+                                   ptr(gw1), ptr(gw2), ptr(gw3), ptr(dT), _lib.stream()), "onr_erb_fold_bwd")
+        return tuple(grads)
+
+
+class _BlockFunction(torch.autograd.Function):
+    """conv3x3 + PixelShuffle + SiLU of ONE block on NCHW fp32 tensors (module-boundary path used when a
+    NeRVBlock is called on its own; the Generator uses the fused executor instead)."""
+
+    @staticmethod
+    def forward(ctx, x, K, bias, stride, cnew):
+        lib = _lib.lib()
+        st = _lib.stream()
+        B, cin, H, W = x.shape
+        s = stride
+        cpi, cpo = pad32(cin), pad32(cnew)
+        nk = s * s * cpo
+        bn, nt = conv_tile_n(nk)
+        npad = bn * nt
+        bn2, nt2 = conv_tile_n(cpi)
+        cpi_rows = bn2 * nt2
+        dev = x.device
+        bf16 = torch.bfloat16
+        train = torch.is_grad_enabled() and (x.requires_grad or K.requires_grad or bias.requires_grad)
+        xh = torch.empty(B, H, W, cpi, dtype=bf16, device=dev)
+        check(lib.onr_nchw_to_nhwc_bf16(ptr(x.detach().contiguous()), B, cin, H, W, cpi, ptr(xh), st), "to_nhwc")
+        wf = torch.empty(9, npad, cpi, dtype=bf16, device=dev)
+        wd = torch.empty(9, cpi_rows, nk, dtype=bf16, device=dev)
+        bias_p = torch.empty(npad, dtype=torch.float32, device=dev)
+        check(lib.onr_pack_weights(ptr(K.detach().contiguous()), ptr(bias.detach().contiguous()), cin, cnew, s,
+                                   npad, cpi_rows, ptr(wf), ptr(wd), ptr(bias_p), st), "onr_pack_weights")
+        y = torch.empty(B, H * s, W * s, cpo, dtype=bf16, device=dev)
+        d = torch.empty_like(y)
+        plan = _conv_plan(lib, kind=_lib.CONV_FPROP_TRAIN, B=B, H=H, W=W, a=ptr(xh), a_cp=cpi, a_s=1,
+                          w=ptr(wf), n_rows=npad, n_total=nk, out=ptr(y), out_cp=cpo, out_s=s, out_d=ptr(d),
+                          bias_p=ptr(bias_p), dmul=None)
+        check(lib.onr_conv_plan_run(plan.handle, st), "onr_conv_plan_run")
+        out = torch.empty(B, cnew, H * s, W * s, dtype=torch.float32, device=dev)
+        check(lib.onr_nhwc_bf16_to_nchw(ptr(y), B, cnew, H * s, W * s, cpo, ptr(out), st), "to_nchw")
+        ctx.geom = (B, cin, H, W, s, cnew, cpi, cpo, nk, cpi_rows)
+        ctx.save_for_backward(xh, d, wd)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.lib()
+        st = _lib.stream()
+        B, cin, H, W, s, cnew, cpi, cpo, nk, cpi_rows = ctx.geom
+        xh, d, wd = ctx.saved_tensors
+        dev, bf16 = gout.device, torch.bfloat16
+        gy = torch.empty(B, H * s, W * s, cpo, dtype=bf16, device=dev)
+        check(lib.onr_nchw_to_nhwc_bf16(ptr(gout.contiguous()), B, cnew, H * s, W * s, cpo, ptr(gy), st), "to_nhwc")
+        dz = gy * d                                   # boundary path only: dZ = dY * SiLU'(z)
+        dKp = torch.zeros(nk, 9, cpi, dtype=torch.float32, device=dev)
+        dbp = torch.zeros(nk, dtype=torch.float32, device=dev)
+        wplan = _wgrad_plan(lib, B=B, H=H, W=W, x=ptr(xh), x_cp=cpi, dz=ptr(dz), dz_cp=cpo, s=s,
+                            dKp=ptr(dKp), dbias_p=ptr(dbp))
+        check(lib.onr_wgrad_plan_run(wplan.handle, st), "onr_wgrad_plan_run")
+        dK = torch.empty(cnew * s * s, cin, 3, 3, dtype=torch.float32, device=dev)
+        db = torch.empty(cnew * s * s, dtype=torch.float32, device=dev)
+        check(lib.onr_unpack_wgrad(ptr(dKp), ptr(dbp), cin, cnew, s, ptr(dK), ptr(db), st), "onr_unpack_wgrad")
+        ones = torch.ones(B, H, W, cpi, dtype=bf16, device=dev)
+        dxh = torch.empty(B, H, W, cpi, dtype=bf16, device=dev)
+        dplan = _conv_plan(lib, kind=_lib.CONV_DGRAD, B=B, H=H, W=W, a=ptr(dz), a_cp=cpo, a_s=s, w=ptr(wd),
+                           n_rows=cpi_rows, n_total=cpi, out=ptr(dxh), out_cp=cpi, out_s=1, out_d=None,
+                           bias_p=None, dmul=ptr(ones))
+        check(lib.onr_conv_plan_run(dplan.handle, st), "onr_conv_plan_run(dgrad)")
+        dx = torch.empty(B, cin, H, W, dtype=torch.float32, device=dev)
+        check(lib.onr_nhwc_bf16_to_nchw(ptr(dxh), B, cin, H, W, cpi, ptr(dx), st), "to_nchw")
+        torch.cuda.current_stream().synchronize()     # plans (TMA descriptors) must outlive the launches
+        return dx, dK, db, None, None
+
+
+class NeRVBlock(nn.Module):
+    """Reference model.py:303-567.  conv3x3(ngf -> new_ngf*stride^2) -> PixelShuffle(stride) -> SiLU."""
+
+    def __init__(self, **kargs):
+        super().__init__()
+        self.ngf, self.new_ngf, self.stride = kargs['ngf'], kargs['new_ngf'], kargs['stride']
+        self.deploy = kargs['deploy']
+        self.branch_type = kargs['branch_type']
+        _require(self.branch_type in SUPPORTED_BRANCHES, f"branch_type {self.branch_type!r}")
+        _require(kargs.get('norm', 'none') == 'none', f"norm {kargs.get('norm')!r}")
+        _require(kargs.get('act', 'swish') == 'swish', f"act {kargs.get('act')!r}")
+        # parameter-free modules kept so that print(model) / module traversal look like the reference
+        self.up_scale = nn.PixelShuffle(self.stride)
+        self.norm = nn.Identity()
+        self.act = nn.SiLU(inplace=True)
+        self.out_channels = self.new_ngf * self.stride * self.stride
+        ci, co = self.ngf, self.out_channels
+        if self.deploy:
+            self.rbr_reparam = nn.Conv2d(ci, co, (3, 3), 1, 1, bias=True)
+        elif self.branch_type == "NeRV_vanilla":
+            self.branch = nn.Conv2d(ci, co, (3, 3), 1, 1, bias=kargs.get('bias', True))
+            _require(self.branch.bias is not None, "bias=False")
+        else:  # ERB: creation order matches reference model.py:324-343 (same RNG consumption)
+            self.rbr_3x3_branch = nn.Conv2d(ci, co, (3, 3), 1, 1)
+            self.rbr_3x1_branch = nn.Conv2d(ci, co, (3, 1), 1, (1, 0))
+            self.rbr_1x3_branch = nn.Conv2d(ci, co, (1, 3), 1, (0, 1))
+            self.rbr_1x1_3x3_1x1_branch_1x1_1 = nn.Conv2d(ci, 2 * ci, (1, 1), 1, 0, bias=False)
+            self.rbr_1x1_3x3_1x1_branch_3x3 = nn.Conv2d(2 * ci, co, (3, 3), 1, 1, bias=False)
+            self.rbr_1x1_3x3_1x1_branch_1x1_2 = nn.Conv2d(co, co, (1, 1), 1, 0, bias=False)
+
+    # ---- structure queries used by the executor -------------------------------------------------
+    def is_erb_train(self):
+        return (not self.deploy) and self.branch_type == "ERB" and hasattr(self, "rbr_3x3_branch")
+
+    def single_conv_name(self):
+        return "rbr_reparam" if (self.deploy or not hasattr(self, "branch")) else "branch"
+
+    def single_conv(self):
+        conv = getattr(self, self.single_conv_name())
+        _fire_prune_hooks(conv)
+        return conv
+
+    # ---- reference API -----------------------------------------------------------------------
+    def get_equivalent_kernel_bias(self):
+        """Reference model.py:450-478; differentiable w.r.t. the nine branch tensors."""
+        if not self.is_erb_train():
+            raise AttributeError("get_equivalent_kernel_bias needs the ERB training branches")
+        b = self
+        return _FoldFunction.apply(
+            b.rbr_3x3_branch.weight, b.rbr_3x3_branch.bias, b.rbr_1x3_branch.weight, b.rbr_1x3_branch.bias,
+            b.rbr_3x1_branch.weight, b.rbr_3x1_branch.bias, b.rbr_1x1_3x3_1x1_branch_1x1_1.weight,
+            b.rbr_1x1_3x3_1x1_branch_3x3.weight, b.rbr_1x1_3x3_1x1_branch_1x1_2.weight)
+
+    def switch_to_deploy(self):
+        """Reference model.py:395-448: fold once into `rbr_reparam`, drop the branches."""
+        if getattr(self, 'deploy', False) or not hasattr(self, 'rbr_3x3_branch'):
+            if hasattr(self, 'rbr_reparam'):
+                self.deploy = True
+            return
+        with torch.no_grad():
+            kernel, bias = self.get_equivalent_kernel_bias()
+        if not hasattr(self, 'rbr_reparam'):
+            self.rbr_reparam = nn.Conv2d(self.ngf, self.out_channels, (3, 3), 1, 1, bias=True)
+        self.rbr_reparam.weight.data = kernel
+        self.rbr_reparam.bias.data = bias
+        for name in _ERB_BRANCHES + ("branch",):
+            if hasattr(self, name):
+                self.__delattr__(name)
+        self.deploy = True
+
+    def forward(self, x):
+        """Reference model.py:518-567 on NCHW fp32 tensors (module-boundary path)."""
+        if self.is_erb_train():
+            K, b = self.get_equivalent_kernel_bias()
+        else:
+            conv = self.single_conv()
+            K, b = conv.weight, conv.bias
+        return _BlockFunction.apply(x, K, b, self.stride, self.new_ngf)
+
+
+class _GeneratorFunction(torch.autograd.Function):
+    """Whole-decoder autograd node: forward = executor.forward, backward = executor.backward."""
+
+    @staticmethod
+    def forward(ctx, gen, ex, embed, *params):
+        img = ex.forward(embed=embed)
+        ctx.gen, ctx.ex = gen, ex
+        return img.clone()
+
+    @staticmethod
+    def backward(ctx, gimg):
+        gen, ex = ctx.gen, ctx.ex
+        grads = gen.alloc_grads()
+        ex.backward(gimg.contiguous(), grads)
+        out = [grads[n] if p.requires_grad else None for n, p in gen.named_parameters()]
+        return (None, None, None) + tuple(out)
+
+
+class Generator(nn.Module):
+    """Reference model.py:571-625."""
+
+    def __init__(self, **kargs):
+        super().__init__()
+        stem_dim, stem_num = [int(x) for x in kargs['stem_dim_num'].split('_')]
+        self.fc_h, self.fc_w, self.fc_dim = [int(x) for x in kargs['fc_hw_dim'].split('_')]
+        _require(stem_num == 1, f"stem_dim_num with {stem_num} hidden layers")
+        _require(kargs.get('act', 'swish') == 'swish', f"act {kargs.get('act')!r}")
+        _require(kargs.get('num_blocks', 1) == 1, "num_blocks > 1")
+        _require(bool(kargs.get('sin_res', True)), "multi-resolution heads (sin_res=False)")
+        _require(kargs.get('bias', True), "bias=False")
+        # reference MLP(): Linear, act, Linear, act with one shared activation module (model.py:184-188)
+        act_fn = nn.SiLU(inplace=True)
+        self.stem = nn.Sequential(nn.Linear(kargs['embed_length'], stem_dim), act_fn,
+                                  nn.Linear(stem_dim, self.fc_h * self.fc_w * self.fc_dim), act_fn)
+        self.layers, self.head_layers = [nn.ModuleList() for _ in range(2)]
+        ngf = self.fc_dim
+        strides = list(kargs['stride_list'])
+        for i, stride in enumerate(strides):
+            if i == 0:
+                new_ngf = int(ngf * kargs['expansion'])
+            else:
+                new_ngf = max(ngf // (1 if stride == 1 else kargs['reduction']), kargs['lower_width'])
+            self.layers.append(NeRVBlock(ngf=ngf, new_ngf=new_ngf, stride=stride, bias=kargs['bias'],
+                                         norm=kargs['norm'], act=kargs['act'], deploy=kargs['deploy'],
+                                         conv_type=kargs.get('conv_type', 'conv'),
+                                         branch_type=kargs['branch_type']))
+            ngf = new_ngf
+            self.head_layers.append(nn.Conv2d(ngf, 3, 1, 1, bias=kargs['bias'])
+                                    if i == len(strides) - 1 else None)
+        self.sigmoid = kargs['sigmoid']
+        self._executors = {}
+
+    # ---- helpers for the executor ---------------------------------------------------------------
+    def head_name(self):
+        return f"head_layers.{len(self.layers) - 1}"
+
+    def head_conv(self):
+        return self.head_layers[len(self.layers) - 1]
+
+    def executor(self, batch, train):
+        key = (batch, bool(train), tuple(b.is_erb_train() for b in self.layers),
+               str(next(self.parameters()).device))
+        ex = self._executors.get(key)
+        if ex is None:
+            ex = NetExecutor(self, batch, train)
+            self._executors = {key: ex}      # one live executor: buffers are large (hundreds of MB)
+        return ex
+
+    def alloc_grads(self):
+        """Zeroed fp32 gradient tensors, one per parameter, carved from a single flat buffer."""
+        named = list(self.named_parameters())
+        total = sum(p.numel() for _, p in named)
+        flat = torch.zeros(total, dtype=torch.float32, device=named[0][1].device)
+        grads, off = {}, 0
+        for n, p in named:
+            grads[n] = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        grads["__flat__"] = flat
+        return grads
+
+    def __deepcopy__(self, memo):
+        # executors hold raw device pointers / TMA descriptors of THIS model's buffers: never copy them
+        # (reference main_train.py:332 deep-copies the model every epoch for the deploy checkpoint)
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_executors" else copy.deepcopy(v, memo)
+        return new
+
+    def forward(self, input):
+        """input: embedding [B, 2*levels] (reference model.py:611-625). Returns [img[B,3,H,W]]."""
+        B = input.size(0)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        ex = self.executor(B, needs_grad)
+        if needs_grad:
+            params = [p for _, p in self.named_parameters()]
+            img = _GeneratorFunction.apply(self, ex, input.detach(), *params)
+        else:
+            with torch.no_grad():
+                img = ex.forward(embed=input).clone()
+        return [img]

@@ -1,0 +1,151 @@
+"""Fast path of the frame-fitting step: one call = the body of the reference hot loop.
+
+Reference main_train.py:229-254, per iteration:
+    embed = PE(norm_idx); data.cuda(); out = model(embed); loss = Fusion6(out, data); adjust_lr();
+    zero_grad(); loss.backward(); optimizer.step(); psnr_fn(); msssim_fn()
+`FrameFitter.step` runs exactly that sequence as liborepnerv.so kernels on persistent buffers with no
+autograd graph, no per-step allocation and no host synchronisation, and (optionally) replays it as ONE
+CUDA graph.  With world_size > 1 every rank fits its own frame (frame-sharded data parallel) and the
+flat fp32 gradient buffer is all-reduced over NCCL before the fused Adam step, which matches the
+reference run with `-b world_size` because every loss term is a batch mean.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, ptr
+from .optim import FusedAdam
+from .utils import _L1_SSIM_LOSSES, lr_multiplier
+
+
+class FrameFitter:
+    def __init__(self, model, pe, args, optimizer=None, world_size=1, steps_per_epoch=None, data_size=None,
+                 use_graph=True, with_msssim=True):
+        self.lib = _lib.lib()
+        self.model, self.pe, self.args = model, pe, args
+        self.world = world_size
+        self.B = args.batchSize
+        if args.loss_type not in _L1_SSIM_LOSSES:
+            raise NotImplementedError(f"loss_type {args.loss_type!r} is outside the B200 hot path")
+        self.w_l1, self.w_ssim = _L1_SSIM_LOSSES[args.loss_type]
+        self.ex = model.executor(self.B, True)
+        dev = self.ex.dev
+        self.dev = dev
+        H, W = self.ex.H, self.ex.W
+        self.H, self.W = H, W
+        # persistent gradients: one flat fp32 buffer, parameters' .grad are views into it
+        self.grads = model.alloc_grads()
+        self.flat_grad = self.grads["__flat__"]
+        for n, p in model.named_parameters():
+            p.grad = self.grads[n]
+        self.opt = optimizer if optimizer is not None else FusedAdam(model.parameters(), lr=args.lr,
+                                                                      betas=(args.beta, 0.999))
+        if not isinstance(self.opt, FusedAdam):
+            raise TypeError("FrameFitter drives orepnerv.optim.FusedAdam")
+        self.opt.fused_zero_grad = True
+        self.opt.grad_scale = 1.0 / world_size
+        self.data_size = data_size if data_size is not None else 1
+        self.steps_per_epoch = steps_per_epoch if steps_per_epoch is not None else self.data_size
+        self.device_sched = args.lr_type in ('cosine', 'const')
+        self.with_msssim = with_msssim and H >= 160 and min(H, W) > 160
+        # static I/O buffers (CUDA-graph friendly)
+        self.frame_u8 = torch.zeros(self.B, 3, H, W, dtype=torch.uint8, device=dev)
+        self.t_norm = torch.zeros(self.B, dtype=torch.float32, device=dev)
+        self.target = torch.zeros(self.B, 3, H, W, dtype=torch.float32, device=dev)
+        self.gimg = torch.zeros(self.B, 3, H, W, dtype=torch.float32, device=dev)
+        self.out = torch.zeros(8, dtype=torch.float32, device=dev)   # loss, l1, ssim, mse, psnr, msssim, lr, -
+        self.loss_work = torch.empty(self.lib.onr_loss_workspace_bytes(self.B, H, W), dtype=torch.uint8, device=dev)
+        self.ms_work = (torch.empty(self.lib.onr_msssim_workspace_bytes(self.B, H, W), dtype=torch.uint8, device=dev)
+                        if self.with_msssim else None)
+        self.freqs = pe.freqs(dev)
+        self.graph = None
+        self.use_graph = use_graph and self.device_sched
+        self.host_step = 0
+        self.launches_per_step = None
+
+    # ------------------------------------------------------------------------------------------
+    def _body(self):
+        lib, st = self.lib, _lib.stream()
+        B, H, W = self.B, self.H, self.W
+        check(lib.onr_frame_u8_to_f32(ptr(self.frame_u8), self.frame_u8.numel(), ptr(self.target), st), "u8_to_f32")
+        img = self.ex.forward(t_norm=self.t_norm, freqs=self.freqs)
+        check(lib.onr_fusion6_fwd_bwd(ptr(img), ptr(self.target), B, H, W, self.w_l1, self.w_ssim, 1.0,
+                                      ptr(self.out), ptr(self.gimg), ptr(self.loss_work), st), "onr_fusion6_fwd_bwd")
+        self.ex.backward(self.gimg, self.grads)
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad)          # NCCL over NVLink; averaged by grad_scale inside Adam
+        lr_dev, step_dev = self.opt.device_scalars(self.dev)
+        if self.device_sched:
+            a = self.args
+            check(lib.onr_sched_tick(ptr(step_dev), ptr(lr_dev), float(a.lr), self.steps_per_epoch, self.data_size,
+                                     int(a.warmup), int(a.epochs), 0 if a.lr_type == 'cosine' else 1, st),
+                  "onr_sched_tick")
+        self.opt.step(device_schedule=self.device_sched)
+        if self.with_msssim:
+            check(lib.onr_msssim(ptr(img), ptr(self.target), B, H, W, ptr(self.out[5:6]), ptr(self.ms_work), st),
+                  "onr_msssim")
+
+    def _host_lr(self):
+        t = self.host_step
+        epoch = (t // self.steps_per_epoch) % self.args.epochs
+        it = t % self.steps_per_epoch
+        lr = self.args.lr * lr_multiplier(epoch, it, self.data_size, self.args)
+        for g in self.opt.param_groups:
+            g['lr'] = lr
+        return lr
+
+    def load_inputs(self, frame_u8, t_norm):
+        """Copies one step's inputs (device or pinned-host tensors) into the static buffers."""
+        self.frame_u8.copy_(frame_u8.reshape(self.frame_u8.shape), non_blocking=True)
+        self.t_norm.copy_(t_norm.reshape(self.t_norm.shape), non_blocking=True)
+
+    def step(self, frame_u8=None, t_norm=None):
+        """One optimisation step on the given frame(s).  Returns the device tensor
+        [loss, L1, SSIM, MSE, PSNR, MS-SSIM, ...] of this step (no host sync)."""
+        if frame_u8 is not None:
+            self.load_inputs(frame_u8, t_norm)
+        lr = self._host_lr()
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+            self.opt._step_count_host += 1
+        else:
+            self._body()
+        self.host_step += 1
+        return self.out
+
+    def _capture(self):
+        # warm-up outside the graph on a side stream (allocations, lazy inits), then capture.
+        # The warm-up runs REAL steps; their effect on parameters/optimizer state is rolled back.
+        params = [p.detach().clone() for p in self.model.parameters()]
+        opt_state = None
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for p, q in zip(self.model.parameters(), params):
+                p.copy_(q)
+            for st in self.opt.state.values():
+                st['exp_avg'].zero_()
+                st['exp_avg_sq'].zero_()
+            self.flat_grad.zero_()
+            _, step_dev = self.opt.device_scalars(self.dev)
+            step_dev.fill_(self.host_step)
+        self.opt._step_count_host = self.host_step
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        # the capture pass itself did not execute; fix the host-side counter it advanced
+        self.opt._step_count_host = self.host_step
+        self.graph = g
+
+    def sync_step_counter(self):
+        """Align the device-side step counter with the host (call after loading a checkpoint)."""
+        _, step_dev = self.opt.device_scalars(self.dev)
+        step_dev.fill_(self.host_step)
+        self.opt._step_count_host = self.host_step

@@ -35,18 +35,23 @@ const char* onr_last_error(void);
 /* 0 when the current device is compute capability 10.x (B200); <0 otherwise.  The library has no
  * other code path: callers must fail loudly when this fails. */
 int onr_check_device(void);
+/* Number of kernels this library has launched in the calling process so far (bench.py's gpu_launches). */
+unsigned long long onr_launch_count(void);
 
 /* ------------------------------------------------------------------ A1+A2: positional encoding + stem
  * utils.py:121-129 (PositionalEncoding.forward), model.py:174-188, 612-613 (stem MLP + view).
  * t_norm[B] (fp32 frame index i/N).  Produces embed[B,2L] (fp32, sin/cos interleaved, rounding order
- * (t*lbase^i)*pi with lbase^i evaluated in double then rounded to fp32 like the reference),
+ * (t*lbase^i)*pi; the host passes freqs[i] = fp32(lbase**i) evaluated in double like the reference),
  * h1[B,hid] = SiLU(W1 e + b1), and the stem output written as NHWC bf16 x0[B,fh,fw,Cp]
- * (value of reference out[b, c*fh*fw + h*fw + w]), plus dstem[B,fh,fw,Cp] = SiLU'(pre-activation). */
-int onr_pe_stem_fwd(const float* t_norm, int B, float lbase, int levels,
+ * (value of reference out[b, c*fh*fw + h*fw + w]), plus dstem[B,fh,fw,Cp] = SiLU'(pre-activation).
+ * t_norm may be NULL: then embed[B,2L] is an INPUT (the reference's Generator.forward(embed) entry). */
+int onr_pe_stem_fwd(const float* t_norm, int B, const float* freqs /* [levels] = fp32(lbase**i) */, int levels,
                     const float* W1, const float* b1, int hid,
                     const float* W2, const float* b2, int fc_dim, int fh, int fw, int Cp,
                     float* embed, float* pre1, float* h1,
                     void* x0_bf16, void* dstem_bf16, void* stream);
+/* utils.py:121-129 alone: embed[B,2L] from t_norm[B] (what PositionalEncoding.forward returns). */
+int onr_pos_encoding(const float* t_norm, int B, const float* freqs, int levels, float* embed, void* stream);
 /* Backward of the stem (autograd of model.py:612 through main_train.py:249).
  * g0[B,fh,fw,Cp] bf16 is dL/d(pre-activation of the 2nd Linear) (SiLU' already applied by the
  * block-0 dgrad epilogue).  Accumulates (+=) into gW1,gb1,gW2,gb2. */
@@ -170,19 +175,32 @@ int onr_msssim(const float* pred, const float* target, int B, int H, int W, floa
  * table: n_tensors entries {param, grad, m, v, numel} as 5 x uint64 each (device array).
  * lr_dev, step_dev: device scalars (lr from adjust_lr, utils.py:240-259; step count t >= 1).
  * grad_scale multiplies grads (1/world_size); grads are zeroed after use when zero_grad != 0. */
-int onr_adam_multi(const uint64_t* table, int n_tensors, size_t total_numel,
+int onr_adam_multi(const uint64_t* table, int n_tensors, size_t max_numel /* largest tensor */,
                    const float* lr_dev, const int* step_dev, float beta1, float beta2, float eps,
                    float grad_scale, int zero_grad, void* stream);
 
+/* adjust_lr (utils.py:240-259) on the device: step_dev += 1, lr_dev = lr0 * multiplier(step) with
+ * cur_epoch = epoch + iter/data_size.  lr_type 0 = cosine, 1 = const; warm-up 0.1 -> 1 over `warmup` epochs. */
+int onr_sched_tick(int* step_dev, float* lr_dev, double lr0, int steps_per_epoch, int data_size,
+                   int warmup, int epochs, int lr_type, void* stream);
+
 /* ------------------------------------------------------------------ A12/A13: eval-side weight transforms
- * main_eval.py:572-587 (global L1 magnitude prune): count of |w| <= thr over a list of tensors. */
-int onr_abs_count_le(const float* w, size_t n, float thr, unsigned long long* count, void* stream);
-int onr_apply_magnitude_mask(float* w, size_t n, float thr, void* stream);
+ * main_eval.py:572-587 (prune.global_unstructured, L1Unstructured): the global k-th smallest |w| is found
+ * by an exact 4-pass radix select over the fp32 bit patterns: hist[256] += histogram of byte
+ * (bits(|w|) >> shift) & 255 over the elements whose bits match `prefix` under `prefix_mask`.
+ * Call once per tensor per pass (hist accumulates); the host picks the bucket between passes. */
+int onr_abs_radix_hist(const float* w, size_t n, uint32_t prefix, uint32_t prefix_mask, int shift,
+                       unsigned long long* hist256, void* stream);
+/* mask[i] = |w[i]| > thr ? 1 : 0 (fp32, like torch's weight_mask); w_out = w * mask. Either may be NULL. */
+int onr_apply_magnitude_mask(const float* w, size_t n, float thr, float* mask, float* w_out, void* stream);
 /* utils.py:11-67 quantize_per_tensor with axis 0 over rows of a [rows, cols] view (axis -1: rows=1):
  * min/max over non-zero entries, scale=(max-min)/2^bit, q=round((t-min)/(scale+1e-19)),
  * new=min+scale*q.  q_out and new_out may alias nothing; either may be NULL. */
 int onr_quant_rows(const float* t, int rows, size_t cols, int bit, float* q_out, float* new_out,
-                   void* stream);
+                   void* scratch /* rows * 8 bytes */, void* stream);
+
+/* uint8 frame (PNG sample) -> fp32 in [0,1], bit-identical to torchvision ToTensor (model.py:64-65). */
+int onr_frame_u8_to_f32(const void* src_u8, size_t n, float* dst, void* stream);
 
 #ifdef __cplusplus
 }

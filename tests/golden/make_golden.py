@@ -1,0 +1,123 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (/root/reference/model.py, utils.py) on
+the CPU of the build container.  The GPU box has no /root/reference: tests only read the committed .pt
+files.  Run:  python tests/golden/make_golden.py
+"""
+import argparse
+import os
+import sys
+from copy import deepcopy
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_shim"))     # pytorch_msssim stand-in (see its docstring)
+sys.path.insert(0, "/root/reference")
+import model as ref_model      # noqa: E402  (reference, unmodified)
+import utils as ref_utils      # noqa: E402  (reference, unmodified)
+
+TINY = dict(embed='1.25_4', stem_dim_num='16_1', fc_hw_dim='3_4_4', expansion=1, reduction=2, lower_width=4,
+            strides=[2, 2])
+SMALL = dict(embed='1.25_40', stem_dim_num='64_1', fc_hw_dim='3_4_12', expansion=1, reduction=2, lower_width=8,
+             strides=[3, 2])
+
+
+def build(cfg, branch_type, deploy=False, seed=1):
+    torch.manual_seed(seed)
+    pe = ref_utils.PositionalEncoding(cfg['embed'])
+    gen = ref_model.Generator(embed_length=pe.embed_length, stem_dim_num=cfg['stem_dim_num'],
+                              fc_hw_dim=cfg['fc_hw_dim'], expansion=cfg['expansion'], num_blocks=1, norm='none',
+                              act='swish', bias=True, reduction=cfg['reduction'], conv_type='conv',
+                              stride_list=cfg['strides'], sin_res=True, lower_width=cfg['lower_width'],
+                              sigmoid=False, deploy=deploy, branch_type=branch_type)
+    return pe, gen
+
+
+def frames(n, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (n, 3, h, w), generator=g).float().div(255)
+
+
+def case(cfg, branch_type, name, n_steps=3):
+    pe, gen = build(cfg, branch_type)
+    out = {'cfg': cfg, 'branch_type': branch_type}
+    out['init_state'] = {k: v.clone() for k, v in gen.state_dict().items()}
+    pos = torch.tensor([0.25, 0.7])
+    embed = pe(pos)
+    out['pos'], out['embed'] = pos, embed.clone()
+    img = gen(embed)[0]
+    out['img'] = img.detach().clone()
+    H, W = img.shape[-2:]
+    target = frames(2, H, W, 7)
+    out['target'] = target
+    if branch_type == 'ERB':
+        out['folded'] = [tuple(t.detach().clone() for t in blk.get_equivalent_kernel_bias()) for blk in gen.layers]
+        dep = deepcopy(gen)
+        for blk in dep.layers:
+            blk.switch_to_deploy()
+        out['deploy_state'] = {k: v.clone() for k, v in dep.state_dict().items()}
+        out['deploy_img'] = dep(embed)[0].detach().clone()
+    args = argparse.Namespace(loss_type='Fusion6', lr=5e-4, lr_type='cosine', warmup=1, epochs=5)
+    loss = ref_utils.loss_fn(img, target, args)
+    out['loss'] = loss.detach().clone()
+    gen.zero_grad()
+    loss.backward()
+    out['grads'] = {k: p.grad.detach().clone() for k, p in gen.named_parameters()}
+    out['psnr'] = ref_utils.psnr_fn([img.detach()], [target]).clone()
+    # a few optimisation steps exactly like reference main_train.py:238-250
+    opt = torch.optim.Adam(gen.parameters(), betas=(0.5, 0.999))
+    gen.zero_grad()
+    losses, lrs = [], []
+    for i in range(n_steps):
+        o = gen(embed)[0]
+        l = ref_utils.loss_fn(o, target, args)
+        lrs.append(ref_utils.adjust_lr(opt, 0, i, 4, args))
+        opt.zero_grad()
+        l.backward()
+        opt.step()
+        losses.append(l.item())
+    out['train_losses'], out['train_lrs'] = losses, lrs
+    out['trained_state'] = {k: v.clone() for k, v in gen.state_dict().items()}
+    torch.save(out, os.path.join(HERE, name))
+    print(name, 'img', tuple(img.shape), 'loss', float(loss), 'params', sum(p.numel() for p in gen.parameters()))
+
+
+def misc():
+    out = {}
+    pe = ref_utils.PositionalEncoding('1.25_40')
+    pos = torch.tensor([0.0, 1 / 132, 0.5, 131 / 132, 599 / 600], dtype=torch.float32)
+    out['pe_pos'], out['pe_embed'] = pos, pe(pos)
+    g = torch.Generator().manual_seed(3)
+    t4 = torch.randn(6, 5, 3, 3, generator=g)
+    t4[t4.abs() < 0.3] = 0
+    t4[2] = 0                       # an all-zero row
+    t2 = torch.randn(7, 9, generator=g)
+    t1 = torch.randn(11, generator=g)
+    out['quant_in'] = {'t4': t4, 't2': t2, 't1': t1}
+    out['quant_out'] = {
+        't4_axis0': ref_utils.quantize_per_tensor(t4, 8, 0), 't4_axis1': ref_utils.quantize_per_tensor(t4, 8, 1),
+        't2_axis0': ref_utils.quantize_per_tensor(t2, 8, 0), 't2_axis-1': ref_utils.quantize_per_tensor(t2, 6, -1),
+        't1_axis-1': ref_utils.quantize_per_tensor(t1, 8, -1),
+    }
+    args = argparse.Namespace(lr=5e-4, lr_type='cosine', warmup=60, epochs=300)
+
+    class _Opt:
+        param_groups = [{'lr': 0.0}]
+    sched = []
+    for epoch, it in [(0, 0), (0, 66), (30, 5), (59, 131), (60, 0), (150, 17), (299, 131)]:
+        sched.append((epoch, it, ref_utils.adjust_lr(_Opt(), epoch, it, 132, args)))
+    out['lr_sched'] = sched
+    # SSIM / MS-SSIM / PSNR metric values through the reference's own call sites (pytorch_msssim is the shim)
+    a = frames(1, 176, 192, 11)
+    b = (a + 0.05 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    out['metric_in'] = (a, b)
+    out['metric_psnr'] = ref_utils.psnr_fn([a], [b])
+    out['metric_msssim'] = ref_utils.msssim_fn([a], [b])
+    torch.save(out, os.path.join(HERE, 'misc.pt'))
+    print('misc.pt written')
+
+
+if __name__ == '__main__':
+    case(TINY, 'ERB', 'tiny_erb.pt')
+    case(TINY, 'NeRV_vanilla', 'tiny_vanilla.pt')
+    case(SMALL, 'ERB', 'small_erb.pt')
+    misc()
