@@ -29,6 +29,7 @@ constexpr int kStageOutBytes = kBlockM * 64;      // one 128 x 32 bf16 staging t
 constexpr int kThreads = 192;
 constexpr int kMaxBlockN = 384;
 constexpr int kSmemBudget = 220 * 1024;
+constexpr int kMaxDynSmem = 232448;   // 227 KB: per-block opt-in maximum on sm_100
 
 struct ConvParams {
     int H, W, B;
@@ -344,13 +345,19 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
         rc = make_act_tmap(&pl->tmD, d->kind == ONR_CONV_FPROP_TRAIN ? d->out_d : d->out, d->B, d->H, d->W,
                            d->out_cp, d->out_s, kTileW, kTileH);
     if (rc) { delete pl; return rc; }
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)pl->smem);
-    if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", pl->smem, cudaGetErrorString(e));
-        delete pl;
-        return (int)e;
+    // The attribute is per function, not per plan: raise it once to the opt-in maximum (227 KB on sm_100).
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kMaxDynSmem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(smem=%d) failed: %s", kMaxDynSmem, cudaGetErrorString(e));
+            delete pl;
+            return (int)e;
+        }
+        attr_set = true;
     }
+    ONR_REQUIRE(pl->smem <= (size_t)kMaxDynSmem, "conv plan needs %zu bytes of shared memory", pl->smem);
     *out = pl;
     return 0;
 }

@@ -145,7 +145,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ K, const float* __
                                     float* __restrict__ bias_p) {
     const int Nk = s * s * Cpo;
     const size_t nwf = (size_t)9 * Npad * Cpi;
-    const size_t nwd = (size_t)9 * Cpi_rows * Nk;
+    const size_t nwd = wd ? (size_t)9 * Cpi_rows * Nk : 0;   // decode-only callers pass wd = NULL
     const size_t total = nwf + nwd + Npad;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {

@@ -255,13 +255,17 @@ int onr_wgrad_plan_create(onr_wgrad_plan** out, const onr_wgrad_desc* d) {
     int rc = make_act_tmap(&pl->tmDz, d->dz, d->B, d->H, d->W, d->dz_cp, d->s, kWgPx, 1);
     if (!rc) rc = make_act_tmap(&pl->tmX, d->x, d->B, d->H, d->W, d->x_cp, 1, kWgPx, 1);
     if (rc) { delete pl; return rc; }
-    cudaError_t e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)pl->smem);
-    if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", pl->smem, cudaGetErrorString(e));
-        delete pl;
-        return (int)e;
+    static bool attr_set = false;   // per-function attribute: raise once to the sm_100 opt-in maximum
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(wgrad smem) failed: %s", cudaGetErrorString(e));
+            delete pl;
+            return (int)e;
+        }
+        attr_set = true;
     }
+    ONR_REQUIRE(pl->smem <= 232448, "wgrad plan needs %zu bytes of shared memory", pl->smem);
     *out = pl;
     return 0;
 }
