@@ -183,7 +183,7 @@ def run_ours(opts):
                     expansion=w['expansion'], num_blocks=1, norm='none', act='swish', bias=True,
                     reduction=w['reduction'], conv_type='conv', stride_list=w['strides'], sin_res=True,
                     lower_width=w['lower_width'], sigmoid=False, deploy=False, branch_type=w['branch_type']).to(dev)
-    n_frames = w['n_frames']
+    n_frames = opts.frames or w['n_frames']
     clip = synthetic_clip(n_frames, w['H'], w['W'], device=dev)                 # uint8, resident in HBM
     spe = sharding.steps_per_epoch(n_frames, world)
     fit = FrameFitter(gen, pe, args, world_size=world, data_size=n_frames, steps_per_epoch=spe,
@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--frames", type=int, default=0, help="clip length override (profiling runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     opts = ap.parse_args()
     if opts.impl == "reference":

@@ -31,6 +31,8 @@ struct GemmArgs {
     int M, N, K;
     Axis am, ak, bk, bn, cm, cn;
     int accumulate;  // C += A*B when non-zero
+    int k_chunk;     // split-K: blockIdx.z handles k in [z*k_chunk, (z+1)*k_chunk); partials are combined
+                     // with atomicAdd (only legal with accumulate != 0, i.e. C already holds its addend)
 };
 
 constexpr int GT = 64, GK = 16;
@@ -41,21 +43,24 @@ __global__ void __launch_bounds__(256) strided_gemm_kernel(const GemmArgs g) {
     const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
     float acc[4][4] = {};
+    const int k_begin = blockIdx.z * g.k_chunk;
+    const int k_end = min(g.K, k_begin + g.k_chunk);
+    const bool split = gridDim.z > 1;
     // loader mapping: 256 threads load 64x16 A and 16x64 B: 4 elements each
-    for (int k0 = 0; k0 < g.K; k0 += GK) {
+    for (int k0 = k_begin; k0 < k_end; k0 += GK) {
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             const int e = threadIdx.x + l * 256;
             {   // A tile: e -> (m = e / 16, k = e % 16)
                 const int m = e / GK, k = e % GK;
                 float v = 0.0f;
-                if (m0 + m < g.M && k0 + k < g.K) v = g.A[axis_off(g.am, m0 + m) + axis_off(g.ak, k0 + k)];
+                if (m0 + m < g.M && k0 + k < k_end) v = g.A[axis_off(g.am, m0 + m) + axis_off(g.ak, k0 + k)];
                 As[k][m] = v;
             }
             {   // B tile: e -> (k = e / 64, n = e % 64)
                 const int k = e / GT, n = e % GT;
                 float v = 0.0f;
-                if (n0 + n < g.N && k0 + k < g.K) v = g.B[axis_off(g.bk, k0 + k) + axis_off(g.bn, n0 + n)];
+                if (n0 + n < g.N && k0 + k < k_end) v = g.B[axis_off(g.bk, k0 + k) + axis_off(g.bn, n0 + n)];
                 Bs[k][n] = v;
             }
         }
@@ -83,13 +88,28 @@ __global__ void __launch_bounds__(256) strided_gemm_kernel(const GemmArgs g) {
             const int n = n0 + tx * 4 + j;
             if (n >= g.N) continue;
             float* c = g.C + axis_off(g.cm, m) + axis_off(g.cn, n);
-            *c = g.accumulate ? *c + acc[i][j] : acc[i][j];
+            if (split) atomicAdd(c, acc[i][j]);
+            else *c = g.accumulate ? *c + acc[i][j] : acc[i][j];
         }
     }
 }
 
-static int launch_gemm(const GemmArgs& g, cudaStream_t st) {
-    dim3 grid(ceil_div(g.N, GT), ceil_div(g.M, GT));
+// allow_split: combine split-K partials with atomics (summation order, hence the last fp32 bits, then varies
+// from run to run).  Used for gradients only; the forward fold stays deterministic so that a deploy
+// checkpoint reproduces the train-state decode bit for bit (reference main_train.py:332-349).
+static int launch_gemm(GemmArgs g, cudaStream_t st, bool allow_split = false) {
+    const int tiles = ceil_div(g.N, GT) * ceil_div(g.M, GT);
+    int splits = 1;
+    if (g.accumulate && allow_split) {
+        // enough CTAs to cover the machine twice, but at least 64 k-elements of work per CTA
+        splits = ceil_div(2 * num_sms(), tiles);
+        const int max_splits = ceil_div(g.K, 64);
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    g.k_chunk = ceil_div(ceil_div(g.K, splits), GK) * GK;
+    splits = ceil_div(g.K, g.k_chunk);
+    dim3 grid(ceil_div(g.N, GT), ceil_div(g.M, GT), splits);
     strided_gemm_kernel<<<grid, 256, 0, st>>>(g);
     ONR_LAUNCH_CHECK();
     return 0;
@@ -227,13 +247,13 @@ int onr_erb_fold_fwd(const float* w3x3, const float* b3x3, const float* w1x3, co
     // T[(o,hw), i] = sum_m W2[o,m,hw] * W1[m,i]
     GemmArgs g1{w2, w1, T, Cout * 9, Cin, C2,
                 ax2(9, (long long)C2 * 9, 1), ax(9), ax(Cin), ax(1),
-                ax2(9, (long long)Cin * 9, 1), ax(9), 0};
+                ax2(9, (long long)Cin * 9, 1), ax(9), 0, 0};
     int rc = launch_gemm(g1, st);
     if (rc) return rc;
     // K[p, (i,hw)] += sum_o W3[p,o] * T[o,(i,hw)]
     GemmArgs g2{w3, T, K, Cout, Cin * 9, Cout,
                 ax(Cout), ax(1), ax((long long)Cin * 9), ax(1),
-                ax((long long)Cin * 9), ax(1), 1};
+                ax((long long)Cin * 9), ax(1), 1, 0};
     return launch_gemm(g2, st);
 }
 
@@ -249,24 +269,24 @@ int onr_erb_fold_bwd(const float* dK, const float* dbias, const float* w1, const
                                                                            g1x3, gb1x3, g3x1, gb3x1);
     ONR_LAUNCH_CHECK();
     // gW3[p,o] += sum_x dK[p,x] T[o,x]
-    GemmArgs a{dK, T, gw3, Cout, Cout, (int)CK, ax(CK), ax(1), ax(1), ax(CK), ax(Cout), ax(1), 1};
-    int rc = launch_gemm(a, st);
+    GemmArgs a{dK, T, gw3, Cout, Cout, (int)CK, ax(CK), ax(1), ax(1), ax(CK), ax(Cout), ax(1), 1, 0};
+    int rc = launch_gemm(a, st, true);
     if (rc) return rc;
     // dT[o,x] = sum_p W3[p,o] dK[p,x]
-    GemmArgs b{w3, dK, dT, Cout, (int)CK, Cout, ax(1), ax(Cout), ax(CK), ax(1), ax(CK), ax(1), 0};
+    GemmArgs b{w3, dK, dT, Cout, (int)CK, Cout, ax(1), ax(Cout), ax(CK), ax(1), ax(CK), ax(1), 0, 0};
     rc = launch_gemm(b, st);
     if (rc) return rc;
     // gW2[(o,hw), m] += sum_i dT[o,i,hw] W1[m,i]
     GemmArgs c{dT, w1, gw2, Cout * 9, C2, Cin,
                ax2(9, CK, 1), ax(9), ax(1), ax(Cin),
-               ax2(9, (long long)C2 * 9, 1), ax(9), 1};
-    rc = launch_gemm(c, st);
+               ax2(9, (long long)C2 * 9, 1), ax(9), 1, 0};
+    rc = launch_gemm(c, st, true);
     if (rc) return rc;
     // gW1[m,i] += sum_{(o,hw)} W2[o,m,hw] dT[o,i,hw]
     GemmArgs d{w2, dT, gw1, C2, Cin, Cout * 9,
                ax(9), ax2(9, (long long)C2 * 9, 1), ax2(9, CK, 1), ax(9),
-               ax(Cin), ax(1), 1};
-    return launch_gemm(d, st);
+               ax(Cin), ax(1), 1, 0};
+    return launch_gemm(d, st, true);
 }
 
 int onr_pack_weights(const float* K, const float* bias, int Cin, int Cnew, int s, int Npad, int Cpi_rows,

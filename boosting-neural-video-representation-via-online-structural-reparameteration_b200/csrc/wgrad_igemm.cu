@@ -175,35 +175,56 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
     }
 }
 
-// Column sums of dZ in the un-shuffled channel order: dbias_p[i*(s*Cp) + jc] += sum_{b,h,w}.
-// One block per (b, shuffled row hs); a row is a [W][s*Cp] matrix whose columns are summed.
-__global__ void dz_colsum_kernel(const __nv_bfloat16* __restrict__ dz, int B, int Hs, int W, int s, int Cp,
-                                 int rows_per_block, float* __restrict__ dbias_p) {
+// Column sums of dZ in the un-shuffled channel order: dbias_p[i*(s*Cp) + jc] += sum_{b,h,w} dZ.
+// For a fixed shuffle-row phase i, each image row is a [W][s*Cp] matrix whose columns are summed.
+// Thread (cg, wl) owns 8 consecutive channels (one 16-byte load) and pixels wl, wl+lanes, ...; four
+// independent loads are in flight per thread.  grid = (row chunks, s, B).
+constexpr int kColsumRows = 2;
+__global__ void __launch_bounds__(256)
+dz_colsum_kernel(const __nv_bfloat16* __restrict__ dz, int Hs, int W, int s, int Cp, float* __restrict__ dbias_p) {
     extern __shared__ float sacc[];  // [s*Cp]
     const int jcn = s * Cp;
-    const int pairs = jcn / 2;
-    const int lanes = blockDim.x / pairs;
-    const int pr = threadIdx.x % pairs, wl = threadIdx.x / pairs;
-    const int i = blockIdx.y;  // shuffle row phase
-    const int b = blockIdx.z;
+    const int groups = jcn / 8;
+    const int lanes = blockDim.x / groups;
+    const int cg = threadIdx.x % groups, wl = threadIdx.x / groups;
+    const int i = blockIdx.y, b = blockIdx.z;
     for (int t = threadIdx.x; t < jcn; t += blockDim.x) sacc[t] = 0.0f;
     __syncthreads();
-    float a0 = 0.0f, a1 = 0.0f;
     if (wl < lanes) {
+        float a[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = 0.0f;
         const int H = Hs / s;
-        const int h_begin = blockIdx.x * rows_per_block;
-        const int h_end = min(H, h_begin + rows_per_block);
-        for (int h = h_begin; h < h_end; ++h) {
-            const uint32_t* rowp = reinterpret_cast<const uint32_t*>(
-                dz + ((size_t)(b * Hs + h * s + i) * (size_t)(W * s)) * Cp);
-            for (int w = wl; w < W; w += lanes) {
-                const uint32_t v = __ldg(rowp + (size_t)w * pairs + pr);
-                a0 += bf16_lo(v);
-                a1 += bf16_hi(v);
+        const int h_end = min(H, (int)(blockIdx.x + 1) * kColsumRows);
+        for (int h = blockIdx.x * kColsumRows; h < h_end; ++h) {
+            const uint4* rowp = reinterpret_cast<const uint4*>(dz + ((size_t)(b * Hs + h * s + i) * (size_t)(W * s)) * Cp);
+            int w = wl;
+            for (; w + 3 * lanes < W; w += 4 * lanes) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(rowp + (size_t)(w + u * lanes) * groups + cg);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t q[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a[2 * e] += bf16_lo(q[e]);
+                        a[2 * e + 1] += bf16_hi(q[e]);
+                    }
+                }
+            }
+            for (; w < W; w += lanes) {
+                const uint4 v = __ldg(rowp + (size_t)w * groups + cg);
+                const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    a[2 * e] += bf16_lo(q[e]);
+                    a[2 * e + 1] += bf16_hi(q[e]);
+                }
             }
         }
-        atomicAdd(&sacc[2 * pr], a0);
-        atomicAdd(&sacc[2 * pr + 1], a1);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&sacc[cg * 8 + e], a[e]);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < jcn; t += blockDim.x) atomicAdd(&dbias_p[i * jcn + t], sacc[t]);
@@ -278,14 +299,11 @@ int onr_wgrad_plan_run(const onr_wgrad_plan* pl, void* stream) {
     ONR_LAUNCH_CHECK();
     if (pl->dbias_p) {
         const int jcn = p.s * pl->dz_cp;
-        const int pairs = jcn / 2;
-        int threads = (256 / pairs) * pairs;
-        if (threads < pairs) threads = pairs;  // pairs <= 320
-        const int rows_per_block = 8;
-        dim3 grid(ceil_div(p.H, rows_per_block), p.s, p.B);
+        const int groups = jcn / 8;                     // <= 80 (s = 5, Cp = 128)
+        const int threads = (256 / groups) * groups;
+        dim3 grid(ceil_div(p.H, kColsumRows), p.s, p.B);
         dz_colsum_kernel<<<grid, threads, jcn * sizeof(float), (cudaStream_t)stream>>>(
-            reinterpret_cast<const __nv_bfloat16*>(pl->dz), p.B, p.H * p.s, p.W, p.s, pl->dz_cp,
-            rows_per_block, pl->dbias_p);
+            reinterpret_cast<const __nv_bfloat16*>(pl->dz), p.H * p.s, p.W, p.s, pl->dz_cp, pl->dbias_p);
         ONR_LAUNCH_CHECK();
     }
     return 0;

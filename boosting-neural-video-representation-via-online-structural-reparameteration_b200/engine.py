@@ -186,15 +186,35 @@ class NetExecutor:
         conv = blk.single_conv()
         return conv.weight.detach(), conv.bias.detach()
 
+    def _side_streams(self):
+        if getattr(self, "_side", None) is None:
+            self._side = [torch.cuda.Stream(device=self.dev) for _ in range(self.L)]
+        return self._side
+
     def refresh_weights(self):
-        """Fold (ERB) and pack every block kernel into the bf16 operand layouts."""
-        st = _lib.stream()
+        """Fold (ERB) and pack every block kernel into the bf16 operand layouts.
+
+        Each block's fold runs on its own side stream (they are independent, small fp32 GEMMs that leave
+        most SMs idle) so the five folds overlap each other and the stem / earlier blocks' convolutions.
+        Returns one event per block; the caller makes the main stream wait on event l before conv l."""
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        events = []
         for l, g in enumerate(self.geoms):
-            K, b = self._block_kernel(l)
-            check(self.lib.onr_pack_weights(
-                ptr(K), ptr(b), g.cin, g.cnew, g.s, g.npad, g.cpi_rows,
-                ptr(self.wf[l]), ptr(self.wd[l]) if self.train else None, ptr(self.bias_p[l]), st),
-                "onr_pack_weights")
+            side = self._side_streams()[l]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                st = _lib.stream()
+                K, b = self._block_kernel(l)
+                check(self.lib.onr_pack_weights(
+                    ptr(K), ptr(b), g.cin, g.cnew, g.s, g.npad, g.cpi_rows,
+                    ptr(self.wf[l]), ptr(self.wd[l]) if self.train else None, ptr(self.bias_p[l]), st),
+                    "onr_pack_weights")
+                ev = torch.cuda.Event()
+                ev.record(side)
+            events.append(ev)
+        return events
 
     # ------------------------------------------------------------------------------------- forward
     def forward(self, embed=None, t_norm=None, freqs=None, refresh=True):
@@ -203,6 +223,7 @@ class NetExecutor:
         gen, st = self.gen, _lib.stream()
         lin1, lin2 = gen.stem[0], gen.stem[2]
         g0 = self.geoms[0]
+        events = self.refresh_weights() if refresh else None     # forks side streams first
         if t_norm is None:
             if embed is None:
                 raise ValueError("forward needs embed or t_norm")
@@ -215,9 +236,10 @@ class NetExecutor:
             gen.fc_dim, gen.fc_h, gen.fc_w, g0.cpi,
             ptr(self.embed), ptr(self.pre1), ptr(self.h1), ptr(self.x[0]), ptr(self.d[0]), st),
             "onr_pe_stem_fwd")
-        if refresh:
-            self.refresh_weights()
+        main = torch.cuda.current_stream()
         for l in range(self.L):
+            if events is not None:
+                main.wait_event(events[l])
             check(self.lib.onr_conv_plan_run(self.fprop[l].handle, st), "onr_conv_plan_run(fprop)")
         head = gen.head_conv()
         check(self.lib.onr_head_fwd(
@@ -241,19 +263,31 @@ class NetExecutor:
             ptr(gimg), ptr(self.img), ptr(self.x[self.L]), ptr(self.d[self.L]), self.B, self.H, self.W,
             self.C_last, gL.cpo, ptr(head.weight), 1 if gen.sigmoid else 0,
             ptr(grads[hname + ".weight"]), ptr(grads[hname + ".bias"]), ptr(self.dz[self.L]), st), "onr_head_bwd")
+        main = torch.cuda.current_stream()
+        joins = []
         for l in reversed(range(self.L)):
             g, blk = self.geoms[l], gen.layers[l]
             check(lib.onr_wgrad_plan_run(self.wgrad[l].handle, st), "onr_wgrad_plan_run")
+            # un-pack + fold backward of block l run on a side stream, overlapped with the remaining dgrads
+            done = torch.cuda.Event()
+            done.record(main)
+            side = self._side_streams()[l]
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                sst = _lib.stream()
+                if blk.is_erb_train():
+                    dK, db = self.dK[l], self.dbias[l]
+                else:   # single-branch block: dK is the parameter gradient itself (grads are zero on entry)
+                    name = f"layers.{l}." + blk.single_conv_name()
+                    dK, db = grads[name + ".weight"], grads[name + ".bias"]
+                check(lib.onr_unpack_wgrad(ptr(self.dKp[l]), ptr(self.dbias_p[l]), g.cin, g.cnew, g.s,
+                                           ptr(dK), ptr(db), sst), "onr_unpack_wgrad")
+                if blk.is_erb_train():
+                    self.scatter_block_grads(l, grads)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                joins.append(ev)
             check(lib.onr_conv_plan_run(self.dgrad[l].handle, st), "onr_conv_plan_run(dgrad)")
-            if blk.is_erb_train():
-                dK, db = self.dK[l], self.dbias[l]
-            else:   # single-branch block: dK is the parameter gradient itself (grads are zero on entry)
-                name = f"layers.{l}." + blk.single_conv_name()
-                dK, db = grads[name + ".weight"], grads[name + ".bias"]
-            check(lib.onr_unpack_wgrad(ptr(self.dKp[l]), ptr(self.dbias_p[l]), g.cin, g.cnew, g.s,
-                                       ptr(dK), ptr(db), st), "onr_unpack_wgrad")
-            if blk.is_erb_train():
-                self.scatter_block_grads(l, grads)
         lin1 = gen.stem[0]
         lin2 = gen.stem[2]
         g0 = self.geoms[0]
@@ -262,6 +296,8 @@ class NetExecutor:
             ptr(lin2.weight), gen.fc_dim, gen.fc_h, gen.fc_w, g0.cpi,
             ptr(grads["stem.0.weight"]), ptr(grads["stem.0.bias"]),
             ptr(grads["stem.2.weight"]), ptr(grads["stem.2.bias"]), ptr(self.dh1), st), "onr_stem_bwd")
+        for ev in joins:
+            main.wait_event(ev)
 
     def scatter_block_grads(self, l, grads):
         """dK/dbias of ERB block l -> gradients of its nine branch tensors (fold backward)."""
