@@ -1,0 +1,187 @@
+"""Pieces shared by main_train.py and main_eval.py: the reference's argparse surface (main_train.py:39-109,
+main_eval.py:31-104), output-directory naming (main_train.py:111-147), the frame source and the model
+factory.  Host-side Python only; nothing here computes on tensors except loading frames.
+"""
+import argparse
+import os
+import re
+import shutil
+
+import torch
+
+from .data import synthetic_clip
+from .model import Generator
+from .utils import PositionalEncoding
+
+
+def build_parser(eval_mode=False):
+    p = argparse.ArgumentParser(fromfile_prefix_chars="@")
+    # dataset parameters
+    p.add_argument('--vid', default=[None], type=int, nargs='+', help='video id list for training')
+    p.add_argument('--scale', type=int, default=1)
+    p.add_argument('--frame_gap', type=int, default=1, help='frame selection gap')
+    p.add_argument('--augment', type=int, default=0)
+    p.add_argument('--dataset', type=str, default='UVG',
+                   help="directory name under ../data (PNG/JPG frames, as in the reference) or "
+                        "'synthetic:<frames>x<H>x<W>' for the built-in synthetic clip")
+    p.add_argument('--test_gap', default=1, type=int, help='evaluation gap')
+    # architecture
+    p.add_argument('--embed', type=str, default='1.25_80')
+    p.add_argument('--stem_dim_num', type=str, default='1024_1')
+    p.add_argument('--fc_hw_dim', type=str, default='9_16_128')
+    p.add_argument('--expansion', type=float, default=8)
+    p.add_argument('--reduction', type=int, default=2)
+    p.add_argument('--strides', type=int, nargs='+', default=[5, 3, 2, 2, 2])
+    p.add_argument('--num_blocks', type=int, default=1)
+    p.add_argument('--norm', default='none', type=str, choices=['none', 'bn', 'in'])
+    p.add_argument('--act', type=str, default='gelu',
+                   choices=['relu', 'leaky', 'leaky01', 'relu6', 'gelu', 'swish', 'softplus', 'hardswish'])
+    p.add_argument('--lower_width', type=int, default=32)
+    p.add_argument("--single_res", action='store_true')
+    p.add_argument("--conv_type", default='conv', type=str, choices=['conv', 'deconv', 'bilinear'])
+    p.add_argument("--branch_type", default='NeRV_vanilla', type=str,
+                   choices=['NeRV_vanilla', 'ERB', 'ACB', 'RepVGG', 'DBB', 'ECB'])
+    # training
+    p.add_argument('-j', '--workers', type=int, default=4)
+    p.add_argument('-b', '--batchSize', type=int, default=1)
+    p.add_argument('--not_resume_epoch', action='store_true')
+    p.add_argument('-e', '--epochs', type=int, default=150)
+    if eval_mode:
+        p.add_argument('--cycles', type=int, default=1)
+        p.add_argument('--finetune', action='store_true', default=False)
+        p.add_argument('--finetune_epochs', type=int, default=10)
+    p.add_argument('--warmup', type=float, default=0.2)
+    p.add_argument('--lr', type=float, default=0.001)
+    p.add_argument('--lr_type', type=str, default='cosine')
+    p.add_argument('--lr_steps', default=[], type=float, nargs="+")
+    p.add_argument('--beta', type=float, default=0.5)
+    p.add_argument('--loss_type', type=str, default='L2')
+    p.add_argument('--lw', type=float, default=1.0)
+    p.add_argument('--sigmoid', action='store_true')
+    # evaluation
+    p.add_argument('--deploy', action='store_true', default=False)
+    p.add_argument('--eval_only', action='store_true', default=False)
+    p.add_argument('--eval_freq', type=int, default=50)
+    p.add_argument('--quant_bit', type=int, default=-1)
+    p.add_argument('--quant_axis', type=int, default=0)
+    p.add_argument('--dump_images', action='store_true', default=False)
+    p.add_argument('--eval_fps', action='store_true', default=False)
+    p.add_argument('--prune_steps', type=float, nargs='+', default=[0., ])
+    p.add_argument('--prune_ratio', type=float, default=1.0)
+    # distributed / misc
+    p.add_argument('--manualSeed', type=int, default=1)
+    p.add_argument('--init_method', default='tcp://127.0.0.1:9888', type=str)
+    p.add_argument('-d', '--distributed', action='store_true', default=False,
+                   help='frame-sharded data parallel; launch with torchrun, one process per GPU')
+    p.add_argument('--debug', action='store_true')
+    p.add_argument('-p', '--print_freq', default=50, type=int)
+    p.add_argument('--weight', default='None', type=str)
+    p.add_argument('--overwrite', action='store_true')
+    p.add_argument('--outf', default='unify')
+    p.add_argument('--suffix', default='')
+    return p
+
+
+def finish_args(args):
+    """Derived fields exactly like reference main_train.py:111-138."""
+    args.warmup = int(args.warmup * args.epochs)
+    if args.debug:
+        args.eval_freq = 1
+        args.outf = 'result/debug'
+    else:
+        args.outf = os.path.join('result', args.outf)
+    args.exp_id = (f'{args.dataset}/embed{args.embed}_{args.stem_dim_num}_fc_{args.fc_hw_dim}__exp{args.expansion}'
+                   f'_reduce{args.reduction}_low{args.lower_width}_blk{args.num_blocks}_gap{args.frame_gap}'
+                   f'_e{args.epochs}_warm{args.warmup}_b{args.batchSize}_{args.conv_type}_lr{args.lr}_{args.lr_type}'
+                   f'_{args.loss_type}_act{args.act}_{args.suffix}')
+    args.outf = os.path.join(args.outf, f'{args.suffix}')
+    return args
+
+
+def prepare_outdir(args, rank=0):
+    if rank == 0:
+        if args.overwrite and os.path.isdir(args.outf) and not args.eval_only:
+            print('Will overwrite the existing output dir!')
+            shutil.rmtree(args.outf)
+        os.makedirs(args.outf, exist_ok=True)
+
+
+def build_model(args, device, deploy=None):
+    pe = PositionalEncoding(args.embed)
+    args.embed_length = pe.embed_length
+    model = Generator(embed_length=args.embed_length, stem_dim_num=args.stem_dim_num, fc_hw_dim=args.fc_hw_dim,
+                      expansion=args.expansion, num_blocks=args.num_blocks, norm=args.norm, act=args.act, bias=True,
+                      reduction=args.reduction, conv_type=args.conv_type, stride_list=args.strides,
+                      sin_res=args.single_res, lower_width=args.lower_width, sigmoid=args.sigmoid,
+                      deploy=args.deploy if deploy is None else deploy, branch_type=args.branch_type)
+    return pe, model.to(device)
+
+
+class FrameCache:
+    """The whole clip as uint8 [N,3,H,W] resident in HBM plus the normalised indices i/N — the on-GPU
+    replacement of reference CustomDataSet (model.py:11-70): same sorted file listing, `vid_list` / `frame_gap`
+    sub-sampling, portrait frames transposed, index i/N.  365 MB for Bunny, 3.7 GB for a 600-frame 1080p clip."""
+
+    def __init__(self, dataset, device, vid_list=(None,), frame_gap=1):
+        m = re.fullmatch(r'synthetic:(\d+)x(\d+)x(\d+)', dataset)
+        if m:
+            n, h, w = (int(x) for x in m.groups())
+            frames = synthetic_clip(n, h, w, device=device)
+        else:
+            frames = self._load_dir(f'../data/{dataset.lower()}', vid_list).to(device)
+        n_all = frames.size(0)
+        idx_all = [float(i) / n_all for i in range(n_all)]                 # reference model.py:37
+        keep = [i for i in range(n_all) if i % frame_gap == 0]              # reference model.py:40-44
+        self.frames = frames[keep].contiguous()
+        self.t = torch.tensor([idx_all[i] for i in keep], dtype=torch.float32, device=device)
+
+    @staticmethod
+    def _load_dir(main_dir, vid_list):
+        import numpy as np
+        from PIL import Image
+        names = sorted(os.listdir(main_dir))
+        if vid_list and vid_list[0] is not None:
+            names = [n for i, n in enumerate(names) if i in set(vid_list)]
+        out = []
+        for n in names:
+            img = np.asarray(Image.open(os.path.join(main_dir, n)).convert('RGB'))
+            t = torch.from_numpy(img.copy()).permute(2, 0, 1)
+            if t.size(1) > t.size(2):                                       # reference model.py:66-67
+                t = t.permute(0, 2, 1)
+            out.append(t)
+        return torch.stack(out).contiguous()
+
+    def __len__(self):
+        return self.frames.size(0)
+
+
+def strip_profiler_keys(state_dict):
+    """thop leaves total_ops / total_params buffers in reference checkpoints (main_eval.py:229-234)."""
+    return {k: v for k, v in state_dict.items() if 'total_ops' not in k and 'total_params' not in k}
+
+
+def huffman_avg_bits(symbols):
+    """Average Huffman code length (bits/symbol) of an integer tensor — the statistic the reference derives
+    with dahuffman.HuffmanCodec.from_data (main_eval.py:673-692).  Returns (avg_bits, total_bits, n_symbols)."""
+    import heapq
+    vals, counts = torch.unique(symbols.reshape(-1), return_counts=True)
+    counts = counts.tolist()
+    if len(counts) == 1:
+        return 1.0, float(counts[0]), 1
+    # dahuffman adds an end-of-file symbol with count 1 to the table
+    heap = [(c, i, None) for i, c in enumerate(counts)] + [(1, len(counts), None)]
+    heapq.heapify(heap)
+    depth = [0] * (len(counts) + 1)
+    groups = {i: [i] for i in range(len(counts) + 1)}
+    nxt = len(counts) + 1
+    while len(heap) > 1:
+        c1, i1, _ = heapq.heappop(heap)
+        c2, i2, _ = heapq.heappop(heap)
+        members = groups.pop(i1) + groups.pop(i2)
+        for mbr in members:
+            depth[mbr] += 1
+        groups[nxt] = members
+        heapq.heappush(heap, (c1 + c2, nxt, None))
+        nxt += 1
+    total_bits = float(sum(c * d for c, d in zip(counts, depth)))
+    return total_bits / sum(counts), total_bits, len(counts)

@@ -191,6 +191,21 @@ class NetExecutor:
             self._side = [torch.cuda.Stream(device=self.dev) for _ in range(self.L)]
         return self._side
 
+    def _weights_key(self):
+        """Identity + version of every tensor the packed operands depend on (decode-time cache key)."""
+        key = []
+        for blk in self.gen.layers:
+            if blk.is_erb_train():
+                ts = [getattr(blk, n).weight for n in ("rbr_3x3_branch", "rbr_1x3_branch", "rbr_3x1_branch",
+                      "rbr_1x1_3x3_1x1_branch_1x1_1", "rbr_1x1_3x3_1x1_branch_3x3", "rbr_1x1_3x3_1x1_branch_1x1_2")]
+                ts += [blk.rbr_3x3_branch.bias, blk.rbr_1x3_branch.bias, blk.rbr_3x1_branch.bias]
+            else:
+                conv = getattr(blk, blk.single_conv_name())
+                ts = ([conv.weight_orig, conv.weight_mask] if hasattr(conv, "weight_orig") else [conv.weight])
+                ts.append(conv.bias)
+            key += [(t.data_ptr(), t._version) for t in ts]
+        return tuple(key)
+
     def refresh_weights(self):
         """Fold (ERB) and pack every block kernel into the bf16 operand layouts.
 
@@ -223,6 +238,11 @@ class NetExecutor:
         gen, st = self.gen, _lib.stream()
         lin1, lin2 = gen.stem[0], gen.stem[2]
         g0 = self.geoms[0]
+        if refresh and not self.train:
+            # decode: re-fold / re-pack only when a parameter changed since the last call
+            key = self._weights_key()
+            refresh = key != getattr(self, "_packed_key", None)
+            self._packed_key = key
         events = self.refresh_weights() if refresh else None     # forks side streams first
         if t_norm is None:
             if embed is None:

@@ -1,0 +1,184 @@
+"""Training driver with the reference's CLI (main_train.py) on top of the B200 hot path.
+
+    python -m orepnerv.main_train -e 300 --lr 0.0005 -b 1 --embed 1.25_40 --stem_dim_num 512_1 \
+        --fc_hw_dim 9_16_26 --expansion 1 --reduction 2 --lower_width 96 --strides 5 2 2 2 2 --single_res \
+        --loss Fusion6 --warmup 0.2 --lr_type cosine --norm none --act swish --branch_type ERB \
+        --dataset synthetic:132x720x1280 --outf bunny --suffix erb
+    torchrun --nproc-per-node 8 -m orepnerv.main_train ... -d          (frame-sharded data parallel)
+
+Kept from the reference: flags and their prefix matching (`--loss` -> `--loss_type`), output directory naming,
+log line formats, per-epoch checkpoint files and their dict layout (main_train.py:292-358): `model_latest.pth`,
+`model_latest_deploy.pth` (folded), `*_train_best*.pth`, `model_val_best.pth`.
+Replaced: the per-step body (main_train.py:229-254) is `FrameFitter.step` — sm_100a kernels on a frame cache
+in HBM, replayed as one CUDA graph; with -d the gradients are all-reduced over NCCL.
+"""
+import os
+import random
+import time
+from copy import deepcopy
+from datetime import datetime
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import sharding
+from .cli_common import FrameCache, build_model, build_parser, finish_args, prepare_outdir
+from .model import NeRVBlock
+from .optim import FusedAdam
+from .trainer import FrameFitter
+from .utils import RoundTensor, frame_stats, msssim_fn
+
+
+def main(argv=None):
+    args = finish_args(build_parser().parse_args(argv))
+    world = int(os.environ.get("WORLD_SIZE", "1")) if args.distributed else 1
+    rank = int(os.environ.get("RANK", "0")) if args.distributed else 0
+    local_rank = int(os.environ.get("LOCAL_RANK", "0")) if args.distributed else 0
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prepare_outdir(args, rank)
+    train(local_rank, rank, world, args)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@torch.no_grad()
+def evaluate(model, cache, pe, args):
+    """Decode every `test_gap`-th frame with the current (train-state) model: reference main_train.py:377-438."""
+    psnrs, msssims, t_fwd = [], [], 0.0
+    model.eval()
+    for i in range(0, len(cache), args.test_gap):
+        embed = pe(cache.t[i:i + 1])
+        torch.cuda.synchronize()
+        t0 = time.time()
+        out = model(embed)
+        torch.cuda.synchronize()
+        t_fwd += time.time() - t0
+        target = cache.frames[i:i + 1].float().div(255)
+        psnrs.append(frame_stats(out[0], target)[4].view(1))
+        msssims.append(msssim_fn(out, [target]).view(1))
+    model.train()
+    n = len(psnrs)
+    return torch.cat(psnrs).mean().view(1), torch.cat(msssims).mean().view(1), n / max(t_fwd, 1e-9)
+
+
+def train(local_rank, rank, world, args):
+    torch.manual_seed(args.manualSeed)
+    np.random.seed(args.manualSeed)
+    random.seed(args.manualSeed)
+    device = torch.device('cuda', local_rank)
+    train_best_psnr, train_best_msssim, val_best_psnr, val_best_msssim = [torch.tensor(0.0) for _ in range(4)]
+    is_train_best = False
+
+    pe, model = build_model(args, device)
+    total_params = sum(p.numel() for p in model.parameters()) / 1e6
+    log_path = '{}/rank{}.txt'.format(args.outf, rank)
+    if rank == 0:
+        print(f'{args}\n {model}\n Model Params: {total_params}M')
+        with open(log_path, 'a') as f:
+            f.write(str(model) + '\n' + f'Params: {total_params}M\n')
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+        writer = SummaryWriter(os.path.join(args.outf, f'param_{total_params}M', 'tensorboard')) if rank == 0 else None
+    except Exception:
+        writer = None
+    print("Use GPU: {} for training".format(local_rank))
+
+    optimizer = FusedAdam(model.parameters(), betas=(args.beta, 0.999))
+    cache = FrameCache(args.dataset, device, vid_list=args.vid, frame_gap=args.frame_gap)
+    data_size = len(cache)                                           # reference: len(train_dataset)
+    spe = sharding.steps_per_epoch(data_size, world * args.batchSize)
+    fitter = FrameFitter(model, pe, args, optimizer=optimizer, world_size=world, steps_per_epoch=spe,
+                         data_size=data_size)
+    B = args.batchSize
+
+    start = datetime.now()
+    for epoch in range(args.epochs):
+        epoch_start = datetime.now()
+        order = sharding.shard_indices(data_size, world, rank, epoch, seed=args.manualSeed) if B == 1 else None
+        stats = []
+        n_steps = spe if not args.debug else min(spe, 11)
+        for i in range(n_steps):
+            if B == 1:
+                idx = torch.tensor([order[i]], device=device)
+            else:
+                perm = sharding.epoch_permutation(data_size, epoch, args.manualSeed)
+                sl = [perm[(i * world * B + rank * B + k) % data_size] for k in range(B)]
+                idx = torch.tensor(sl, device=device)
+            out = fitter.step(cache.frames[idx], cache.t[idx])
+            stats.append(out[:6].clone())
+            if i % args.print_freq == 0 or i == n_steps - 1:
+                st = torch.stack(stats).mean(0).cpu()
+                lr = fitter.opt.param_groups[0]['lr']
+                print_str = '[{}] Rank:{}, Epoch[{}/{}], Step [{}/{}], lr:{:.2e} PSNR: {}, MSSSIM: {}'.format(
+                    datetime.now().strftime("%Y/%m/%d %H:%M:%S"), local_rank, epoch + 1, args.epochs, i + 1, n_steps,
+                    lr, RoundTensor(st[4:5], 2, False), RoundTensor(st[5:6], 4, False))
+                print(print_str, flush=True)
+                if rank == 0:
+                    with open(log_path, 'a') as f:
+                        f.write(print_str + '\n')
+        st = torch.stack(stats).mean(0).cpu()
+        train_psnr, train_msssim = st[4:5], st[5:6]
+        if rank == 0:
+            h, w = fitter.H, fitter.W
+            is_train_best = bool(train_psnr[-1] > train_best_psnr)
+            train_best_psnr = train_psnr[-1] if is_train_best else train_best_psnr
+            train_best_msssim = train_msssim[-1] if train_msssim[-1] > train_best_msssim else train_best_msssim
+            if writer is not None:
+                writer.add_scalar(f'Train/PSNR_{h}X{w}_gap{args.frame_gap}', train_psnr[-1].item(), epoch + 1)
+                writer.add_scalar(f'Train/MSSSIM_{h}X{w}_gap{args.frame_gap}', train_msssim[-1].item(), epoch + 1)
+                writer.add_scalar('Train/lr', fitter.opt.param_groups[0]['lr'], epoch + 1)
+            now = datetime.now()
+            print_str = '\t{}p: current: {:.2f}\t best: {:.2f}\t msssim_best: {:.4f}\t'.format(
+                h, train_psnr[-1].item(), float(train_best_psnr), float(train_best_msssim))
+            print_str += "Time/epoch: \tCurrent:{:.2f} \tAverage:{:.2f}".format(
+                (now - epoch_start).total_seconds(), (now - start).total_seconds() / (epoch + 1))
+            print(print_str, flush=True)
+            with open(log_path, 'a') as f:
+                f.write(print_str + '\n')
+
+        save_checkpoint = {
+            'epoch': epoch + 1, 'state_dict': model.state_dict(), 'train_best_psnr': train_best_psnr,
+            'train_best_msssim': train_best_msssim, 'val_best_psnr': val_best_psnr,
+            'val_best_msssim': val_best_msssim, 'optimizer': optimizer.state_dict()}
+
+        if (epoch + 1) % args.eval_freq == 0 or epoch > args.epochs - 10:
+            val_psnr, val_msssim, fps = evaluate(model, cache, pe, args)
+            if rank == 0:
+                is_val_best = bool(val_psnr[-1] > val_best_psnr)
+                val_best_psnr = val_psnr[-1] if is_val_best else val_best_psnr
+                val_best_msssim = val_msssim[-1] if val_msssim[-1] > val_best_msssim else val_best_msssim
+                print_str = f'Eval best_PSNR at epoch{epoch + 1}:'
+                print_str += '\t{}p: current: {:.2f}\tbest: {:.2f} \tbest_msssim: {:.4f}\t decode fps: {:.1f}'.format(
+                    fitter.H, val_psnr[-1].item(), float(val_best_psnr), float(val_best_msssim), fps)
+                print(print_str)
+                with open(log_path, 'a') as f:
+                    f.write(print_str + '\n')
+                if is_val_best:
+                    torch.save(save_checkpoint, '{}/model_val_best.pth'.format(args.outf))
+
+        if rank == 0:
+            torch.save(save_checkpoint, '{}/model_latest.pth'.format(args.outf))
+            if is_train_best:
+                torch.save(save_checkpoint, '{}/model_train_best.pth'.format(args.outf))
+            if args.branch_type == 'ERB':
+                copy_model = deepcopy(model)
+                for layer in copy_model.layers:
+                    if isinstance(layer, NeRVBlock):
+                        layer.switch_to_deploy()
+                deploy_checkpoint = dict(save_checkpoint, state_dict=copy_model.state_dict())
+                torch.save(deploy_checkpoint, '{}/model_latest_deploy.pth'.format(args.outf))
+                if is_train_best:
+                    torch.save(deploy_checkpoint, '{}/model_train_best_deploy.pth'.format(args.outf))
+                if epoch == args.epochs - 1:
+                    n_dep = sum(p.numel() for p in copy_model.parameters()) / 1e6
+                    with open(log_path, 'a') as f:
+                        f.write(f'Deploy Rep-Model Params: {n_dep:.3f}M\n')
+    if rank == 0:
+        print("Training complete in: " + str(datetime.now() - start))
+
+
+if __name__ == '__main__':
+    main()

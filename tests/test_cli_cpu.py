@@ -1,0 +1,55 @@
+"""CPU tests of the CLI layer: the reference's argparse surface (prefix matching included), derived fields,
+and the Huffman code-length statistic that replaces dahuffman."""
+import heapq
+
+import torch
+
+from orepnerv.cli_common import build_parser, finish_args, huffman_avg_bits, strip_profiler_keys
+
+README_FLAGS = ("-e 300 --lr 0.0005 -b 1 --embed 1.25_40 --stem_dim_num 512_1 --fc_hw_dim 9_16_26 --expansion 1 "
+                "--reduction 2 --lower_width 96 --strides 5 2 2 2 2 --num_blocks 1 --single_res --loss Fusion6 "
+                "--warmup 0.2 --lr_type cosine --norm none --act swish --branch_type ERB --outf bunny --suffix erb "
+                "--dataset bunny").split()
+
+
+def test_readme_command_line_parses_like_the_reference():
+    args = finish_args(build_parser().parse_args(README_FLAGS))
+    assert args.loss_type == 'Fusion6'                 # `--loss` resolves by prefix (reference README.md:49)
+    assert args.warmup == 60 and args.epochs == 300    # int(0.2 * 300), reference main_train.py:111
+    assert args.outf == 'result/bunny/erb'
+    assert args.strides == [5, 2, 2, 2, 2] and args.single_res and args.branch_type == 'ERB'
+    ev = finish_args(build_parser(eval_mode=True).parse_args(README_FLAGS + ['--prune_ratio', '0.2', '--quant_bit', '8']))
+    assert ev.prune_ratio == 0.2 and ev.quant_bit == 8 and ev.finetune is False
+
+
+def test_strip_profiler_keys():
+    sd = {'stem.0.weight': 1, 'total_ops': 2, 'layers.0.total_params': 3}
+    assert list(strip_profiler_keys(sd)) == ['stem.0.weight']
+
+
+def _huffman_lengths(counts):
+    heap = [(c, i, [i]) for i, c in enumerate(counts)]
+    heapq.heapify(heap)
+    depth = [0] * len(counts)
+    nxt = len(counts)
+    while len(heap) > 1:
+        c1, _, m1 = heapq.heappop(heap)
+        c2, _, m2 = heapq.heappop(heap)
+        for m in m1 + m2:
+            depth[m] += 1
+        heapq.heappush(heap, (c1 + c2, nxt, m1 + m2))
+        nxt += 1
+    return depth
+
+
+def test_huffman_avg_bits():
+    g = torch.Generator().manual_seed(0)
+    sym = torch.randint(0, 40, (5000,), generator=g).float()
+    sym[:2000] = 7.0
+    avg, total, n = huffman_avg_bits(sym)
+    vals, counts = torch.unique(sym, return_counts=True)
+    depth = _huffman_lengths(counts.tolist() + [1])          # + dahuffman's EOF symbol
+    expect = sum(c * d for c, d in zip(counts.tolist(), depth))
+    assert n == len(vals) and abs(avg - expect / 5000) < 1e-12
+    p = counts.double() / counts.sum()
+    assert avg >= float(-(p * p.log2()).sum()) - 1e-9

@@ -383,3 +383,28 @@ def test_s720_properties(dev):
     for op in ("fprop", "dgrad", "wgrad"):
         r = subprocess.run([exe, op, "l3", "0"], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_cli_train_then_eval(dev, tmp_path, monkeypatch):
+    """README workflow end to end at toy size: main_train (ERB, synthetic clip) writes the reference's checkpoint
+    files; main_eval loads the deploy checkpoint, prunes 20 %, quantises to 8 bit and decodes."""
+    from orepnerv import main_train, main_eval
+    monkeypatch.chdir(tmp_path)
+    flags = ("-e 3 --lr 0.002 -b 1 --embed 1.25_40 --stem_dim_num 64_1 --fc_hw_dim 3_4_12 --expansion 1 --reduction 2 "
+             "--lower_width 8 --strides 3 2 --single_res --loss Fusion6 --warmup 0.2 --lr_type cosine --norm none "
+             "--act swish --branch_type ERB --outf toy --suffix erb --dataset synthetic:6x18x24 --eval_freq 1 -p 100"
+             ).split()
+    main_train.main(flags + ['--overwrite'])
+    out = tmp_path / 'result' / 'toy' / 'erb'
+    for f in ('model_latest.pth', 'model_latest_deploy.pth', 'model_train_best.pth', 'model_val_best.pth', 'rank0.txt'):
+        assert (out / f).exists(), f
+    ck = torch.load(out / 'model_latest.pth', weights_only=True)
+    assert set(ck) == {'epoch', 'state_dict', 'train_best_psnr', 'train_best_msssim', 'val_best_psnr',
+                       'val_best_msssim', 'optimizer'}
+    assert 'layers.0.rbr_1x1_3x3_1x1_branch_3x3.weight' in ck['state_dict']
+    dk = torch.load(out / 'model_latest_deploy.pth', weights_only=True)
+    assert 'layers.0.rbr_reparam.weight' in dk['state_dict'] and 'layers.0.rbr_3x3_branch.weight' not in dk['state_dict']
+    psnr_full, _ = main_eval.main(flags + ['--eval_only'])
+    psnr_pq, _ = main_eval.main(flags + ['--eval_only', '--prune_ratio', '0.2', '--quant_bit', '8'])
+    assert psnr_full > 5.0 and psnr_pq > 5.0 and abs(psnr_full - psnr_pq) < 3.0
+    assert (out / 'only_prune0.20_quant8.txt').exists() and (out / 'bpp_rank0.txt').exists()
