@@ -155,6 +155,11 @@ def run_reference(opts):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def _mark(msg):
+    if os.environ.get("ONR_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(opts):
     import torch
     import torch.distributed as dist
@@ -175,6 +180,7 @@ def run_ours(opts):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
+    _mark("process group + library ready")
     w = WORKLOAD
     args = make_args(world)
     torch.manual_seed(1)
@@ -200,11 +206,13 @@ def run_ours(opts):
             dist.barrier()
         torch.cuda.synchronize()
 
+    _mark("model, clip and fitter built")
     # ---------------- device-resident timing (`value`) ----------------
     it = iter(order)
     for _ in range(opts.warmup):
         i = next(it)
         fit.step(clip[i:i + 1], t_all[i:i + 1])
+    _mark("warm-up done")
     barrier()
     launches0 = lib.onr_launch_count()
     sampler = ClockSampler(local_rank)
@@ -227,6 +235,7 @@ def run_ours(opts):
         ms = tms.item()
     value = world * opts.steps / (ms / 1000.0)
 
+    _mark(f"timed region done: {ms:.2f} ms")
     # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
     pinned_frames = [clip[i:i + 1].cpu().pin_memory() for i in order[:8]]
     pinned_t = [(torch.tensor([i], dtype=torch.float32) / n_frames).pin_memory() for i in order[:8]]
@@ -249,6 +258,7 @@ def run_ours(opts):
         ms_e2e = tms.item()
     e2e = world * opts.steps / (ms_e2e / 1000.0)
 
+    _mark("e2e done")
     # ---------------- kernels per step (claimed gpu_launches) ----------------
     c0 = lib.onr_launch_count()
     fit._body()

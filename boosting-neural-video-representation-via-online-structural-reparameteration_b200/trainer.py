@@ -65,6 +65,13 @@ class FrameFitter:
 
     # ------------------------------------------------------------------------------------------
     def _body(self):
+        self._body_pre()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad)          # NCCL over NVLink; averaged by grad_scale inside Adam
+        self._body_post()
+
+    def _body_pre(self):
+        """frame conversion, forward, loss + its gradient, backward -> local gradients in self.flat_grad"""
         lib, st = self.lib, _lib.stream()
         B, H, W = self.B, self.H, self.W
         check(lib.onr_frame_u8_to_f32(ptr(self.frame_u8), self.frame_u8.numel(), ptr(self.target), st), "u8_to_f32")
@@ -72,8 +79,12 @@ class FrameFitter:
         check(lib.onr_fusion6_fwd_bwd(ptr(img), ptr(self.target), B, H, W, self.w_l1, self.w_ssim, 1.0,
                                       ptr(self.out), ptr(self.gimg), ptr(self.loss_work), st), "onr_fusion6_fwd_bwd")
         self.ex.backward(self.gimg, self.grads)
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad)          # NCCL over NVLink; averaged by grad_scale inside Adam
+
+    def _body_post(self):
+        """LR schedule tick, fused Adam (+ gradient averaging and zeroing), MS-SSIM metric"""
+        lib, st = self.lib, _lib.stream()
+        B, H, W = self.B, self.H, self.W
+        img = self.ex.img
         lr_dev, step_dev = self.opt.device_scalars(self.dev)
         if self.device_sched:
             a = self.args
@@ -109,6 +120,11 @@ class FrameFitter:
             if self.graph is None:
                 self._capture()
             self.graph.replay()
+            if self.world > 1:
+                # the collective stays outside the graphs: graph 1 = up to the local gradients, eager NCCL
+                # all-reduce, graph 2 = schedule tick + Adam + metrics
+                dist.all_reduce(self.flat_grad)
+                self.graph_post.replay()
             self.opt._step_count_host += 1
         else:
             self._body()
@@ -119,7 +135,9 @@ class FrameFitter:
         # warm-up outside the graph on a side stream (allocations, lazy inits), then capture.
         # The warm-up runs REAL steps; their effect on parameters/optimizer state is rolled back.
         params = [p.detach().clone() for p in self.model.parameters()]
-        opt_state = None
+        for gi, group in enumerate(self.opt.param_groups):
+            self.opt._table(gi, group)                       # materialise exp_avg / exp_avg_sq
+        moments = [(st['exp_avg'].clone(), st['exp_avg_sq'].clone()) for st in self.opt.state.values()]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -130,16 +148,25 @@ class FrameFitter:
         with torch.no_grad():
             for p, q in zip(self.model.parameters(), params):
                 p.copy_(q)
-            for st in self.opt.state.values():
-                st['exp_avg'].zero_()
-                st['exp_avg_sq'].zero_()
+            for st, (m0, v0) in zip(self.opt.state.values(), moments):
+                st['exp_avg'].copy_(m0)
+                st['exp_avg_sq'].copy_(v0)
             self.flat_grad.zero_()
             _, step_dev = self.opt.device_scalars(self.dev)
             step_dev.fill_(self.host_step)
         self.opt._step_count_host = self.host_step
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._body()
+        if self.world == 1:
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph_post = None
+        else:
+            with torch.cuda.graph(g):
+                self._body_pre()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self._body_post()
+            self.graph_post = g2
         # the capture pass itself did not execute; fix the host-side counter it advanced
         self.opt._step_count_host = self.host_step
         self.graph = g
