@@ -65,6 +65,8 @@ _SIGNATURES = {
     "onr_conv_plan_create": (i32, [C.POINTER(vp), C.POINTER(ConvDesc)]),
     "onr_conv_plan_run": (i32, [vp, vp]),
     "onr_conv_plan_destroy": (None, [vp]),
+    "onr_conv_plan_info": (i32, [vp] + [C.POINTER(i32)] * 5),
+    "onr_conv_plan_set_prof": (i32, [vp, vp, C.POINTER(i32)]),
     "onr_conv_tile_n": (i32, [i32, C.POINTER(i32), C.POINTER(i32)]),
     "onr_wgrad_plan_create": (i32, [C.POINTER(vp), C.POINTER(WgradDesc)]),
     "onr_wgrad_plan_run": (i32, [vp, vp]),

@@ -189,7 +189,29 @@ static int run_conv(const Shape& sh, int kind, int reps, bool check) {
         CK(cudaEventElapsedTime(&ms, e0, e1));
         ms /= reps;
         const double flop = 2.0 * px * (double)n_total * 9.0 * k_tap;
-        printf("  time %.3f ms  %.1f TFLOP/s (block_n %d x %d tiles)\n", ms, flop / ms * 1e-9, block_n, n_tiles);
+        if (getenv("ONR_PROF")) {
+            int grid = 0;
+            OK(onr_conv_plan_set_prof(plan, nullptr, &grid));
+            long long* pd;
+            CK(cudaMalloc(&pd, (size_t)grid * 8 * sizeof(long long)));
+            CK(cudaMemset(pd, 0, (size_t)grid * 8 * sizeof(long long)));
+            OK(onr_conv_plan_set_prof(plan, pd, &grid));
+            OK(onr_conv_plan_run(plan, 0));
+            CK(cudaDeviceSynchronize());
+            std::vector<long long> hp((size_t)grid * 8);
+            CK(cudaMemcpy(hp.data(), pd, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            double acc[8] = {0};
+            for (int c = 0; c < grid; ++c)
+                for (int j = 0; j < 8; ++j) acc[j] += (double)hp[(size_t)c * 8 + j] / grid;
+            printf("  prof (avg cycles per CTA over %d CTAs, %.1f tiles each): total %.0f | MMA waits: A %.0f  W %.0f  acc %.0f"
+                   " | epilogue: wait acc %.0f  wait store %.0f  busy %.0f\n", grid, acc[7], acc[0], acc[1], acc[2], acc[3],
+                   acc[4], acc[5], acc[6]);
+            OK(onr_conv_plan_set_prof(plan, nullptr, &grid));
+        }
+        int pbn, pnt, pms, pna, pnb;
+        OK(onr_conv_plan_info(plan, &pbn, &pnt, &pms, &pna, &pnb));
+        printf("  time %.3f ms  %.1f TFLOP/s (block_n %d x %d n-tiles, %d sub-tiles, rings A%d B%d)\n", ms,
+               flop / ms * 1e-9, pbn, pnt, pms, pna, pnb);
     }
     onr_conv_plan_destroy(plan);
     return ok ? 0 : 1;

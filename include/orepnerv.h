@@ -118,6 +118,11 @@ typedef struct {
 int onr_conv_plan_create(onr_conv_plan** plan, const onr_conv_desc* desc);
 int onr_conv_plan_run(const onr_conv_plan* plan, void* stream);
 void onr_conv_plan_destroy(onr_conv_plan* plan);
+/* Tiling a plan chose: N tile, number of N tiles, 128-pixel sub-tiles per CTA tile, A / weight ring depths. */
+int onr_conv_plan_info(const onr_conv_plan* plan, int* block_n, int* n_tiles, int* ms, int* na, int* nb);
+/* Test/profiling hook: per-CTA cycle counters (8 x int64 per CTA: total, MMA wait A, MMA wait weights, MMA wait
+ * accumulator, epilogue wait accumulator, epilogue wait store, epilogue busy, tiles); NULL switches it off. */
+int onr_conv_plan_set_prof(onr_conv_plan* plan, long long* prof_dev, int* grid);
 /* block_n / n_tiles the plan will use for a given N, so callers can size packed weights. */
 int onr_conv_tile_n(int n_total, int* block_n, int* n_tiles);
 

@@ -26,11 +26,11 @@ def test_library_exports_every_declared_symbol():
 
 def test_tile_n_rule():
     from orepnerv.engine import conv_tile_n
-    assert conv_tile_n(384) == (384, 1)
+    assert conv_tile_n(384) == (192, 2)
     assert conv_tile_n(96) == (96, 1)
-    assert conv_tile_n(800) == (288, 3)
-    assert conv_tile_n(864) == (288, 3)
-    assert conv_tile_n(3200) == (384, 9)
+    assert conv_tile_n(800) == (160, 5)
+    assert conv_tile_n(864) == (224, 4)
+    assert conv_tile_n(3200) == (256, 13)
     lib = _lib.load()
     assert lib.onr_conv_tile_n(33, None, None) < 0        # not a multiple of 32 -> error code, message set
     assert b"multiple of 32" in lib.onr_last_error()
