@@ -24,7 +24,7 @@ NVCC_FLAGS = [
 
 LIB_SOURCES = [s for s in [
     "onr_api.cu", "conv_igemm.cu", "wgrad_igemm.cu", "conv_simt.cu", "fold.cu", "stem.cu", "head.cu",
-    "loss_ssim.cu", "adam.cu", "evalops.cu",
+    "loss_ssim.cu", "adam.cu", "evalops.cu", "mma_bench.cu",
 ] if os.path.exists(os.path.join(CSRC, s))]
 
 

@@ -17,10 +17,15 @@
 // * MS sub-tiles (stacked vertically, MS*block_n <= 512 TMEM columns) share every weight tile: the weights
 //   are streamed once per MS*128 pixels instead of once per 128.
 // * A boxes and weight tiles travel through two independent mbarrier rings fed by two producer warps.
-// * warp 0 = A producer, warp 1 = UMMA issuer (one thread), warp 2 = weight producer, warps 3..6 = epilogue
-//   (tcgen05.ld -> bias/SiLU/SiLU' or dgrad scaling -> bf16 -> swizzled smem -> TMA store through the
-//   PixelShuffle view, so the shuffle is pure addressing).
-// * persistent: grid = min(tiles, #SM); TMEM double-buffered when 2*MS*block_n <= 512.
+// * K advances in 64-channel chunks with 128-byte rows / SWIZZLE_128B wherever the channel count allows and
+//   a 32-channel / SWIZZLE_64B tail otherwise (96 = 64 + 32).  Cycle counters on v2
+//   (profiles/r01_conv_v2_role_cycle_counters.txt) showed the UMMA operand fetch from 64-byte-swizzled rows
+//   running at ~53 B/clk, i.e. the tensor pipe idling on shared memory; 128-byte rows double that.
+// * warp 0 = A producer, warp 1 = UMMA issuer (one thread), warp 2 = weight producer, warps 3..10 = epilogue
+//   (two warps per TMEM lane quarter: tcgen05.ld -> bias/SiLU/SiLU' or dgrad scaling -> bf16 -> swizzled smem
+//   -> TMA store through the PixelShuffle view, so the shuffle is pure addressing).
+// * persistent: grid = min(tiles, #SM); the accumulator is ALWAYS double-buffered in TMEM
+//   (2*MS*block_n <= 512) so the epilogue of tile t overlaps the MMAs of tile t+1.
 #include "onr_common.cuh"
 #include "onr_ptx.cuh"
 
@@ -30,10 +35,15 @@ namespace onr {
 
 constexpr int kSubH = 16;                          // sub-tile: 16 x 8 pixels = 128 accumulator rows
 constexpr int kSubW = 8;
-constexpr int kChunkK = 32;                        // bf16 elements per K step (64 bytes)
-constexpr int kRowBytes = kSubW * 64;              // one image row of a box = 512 B = SWIZZLE_64B repeat
-constexpr int kStageOutBytes = 128 * 64;           // one 128 x 32 bf16 staging tile
-constexpr int kThreads = 224;
+constexpr int kStageOutBytes = 128 * 128;          // one 128 x 64 bf16 staging tile (or two 128 x 32 tiles)
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+// Warp roles: warps 0..7 = epilogue, 8 = A producer, 9 = weight producer, 10.. = UMMA issuers (warp 10 also owns
+// the TMEM allocation).
+constexpr int kWarpProdA = 8, kWarpProdB = 9, kWarpMma0 = 10;
+constexpr int kMaxIssuers = 2;                     // UMMA issuer warps (alternate K-groups of a tile)
+constexpr int kWarpMma = kWarpMma0;                // TMEM owner
+constexpr int kThreads = (kWarpMma0 + kMaxIssuers) * 32;
 constexpr int kMaxBlockN = 256;
 constexpr int kMaxMS = 4;
 constexpr int kMaxDynSmem = 232448;                // 227 KB: per-block opt-in maximum on sm_100
@@ -43,8 +53,8 @@ struct ConvParams {
     int H, W, B;
     int tiles_w, tiles_h, n_tiles, total_tiles;
     int block_n, ms;
-    int chunks, jc_chunks, sign;
-    int n_total, acc_bufs;
+    int chunks, cpi, n64, cj, sign;   // chunks per tap, chunks per shuffle row i, 64-wide chunks per i, channels per i
+    int n_total, acc_bufs, issuers;
     int na, nb;              // ring depths
     int a_bytes, b_bytes;    // slot sizes
     int mode;
@@ -61,7 +71,7 @@ __device__ __forceinline__ long long clk() { return clock64(); }
 struct __align__(8) SmemBarriers {
     uint64_t a_full[kMaxRing], a_empty[kMaxRing];
     uint64_t b_full[kMaxRing], b_empty[kMaxRing];
-    uint64_t tmem_full[2], tmem_empty[2];
+    uint64_t tmem_full[2], tmem_empty[2], tile_started[2];
     uint32_t tmem_base;
 };
 
@@ -69,6 +79,18 @@ __device__ __forceinline__ float tanh_approx(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+struct Chunk {
+    int ii, jc0, width;
+};
+__device__ __forceinline__ Chunk chunk_of(const ConvParams& p, int ch) {
+    Chunk c;
+    c.ii = ch / p.cpi;
+    const int k = ch - c.ii * p.cpi;
+    c.width = k < p.n64 ? 64 : 32;
+    c.jc0 = k < p.n64 ? k * 64 : p.n64 * 64;
+    return c;
 }
 
 struct TileCoord {
@@ -89,8 +111,10 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmD,
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmA32,
+                  const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmB32,
+                  const __grid_constant__ CUtensorMap tmY64, const __grid_constant__ CUtensorMap tmY32,
+                  const __grid_constant__ CUtensorMap tmD64, const __grid_constant__ CUtensorMap tmD32,
                   const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [na x A slot] [nb x B slot] [staging 2 x 2 x 8 KB] [barriers]
@@ -112,18 +136,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(smem_u32(&bars->b_empty[s]), 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(smem_u32(&bars->tmem_full[b]), 1);
-            mbar_init(smem_u32(&bars->tmem_empty[b]), 128);
+            mbar_init(smem_u32(&bars->tmem_full[b]), p.issuers);
+            mbar_init(smem_u32(&bars->tile_started[b]), 1);
+            mbar_init(smem_u32(&bars->tmem_empty[b]), kEpiThreads);
         }
         fence_mbar_init();
     }
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmY);
-        if (p.mode == ONR_CONV_FPROP_TRAIN) tma_prefetch_desc(&tmD);
+    if (warp == kWarpProdA && lane == 0) {
+        tma_prefetch_desc(&tmA64);
+        tma_prefetch_desc(&tmA32);
+        tma_prefetch_desc(&tmY64);
+        tma_prefetch_desc(&tmY32);
     }
-    if (warp == 2 && lane == 0) tma_prefetch_desc(&tmB);
-    if (warp == 1) {
+    if (warp == kWarpProdB && lane == 0) {
+        tma_prefetch_desc(&tmB64);
+        tma_prefetch_desc(&tmB32);
+    }
+    if (warp == kWarpMma) {
         tmem_alloc(smem_u32(&bars->tmem_base), 512);
         tmem_relinquish();
     }
@@ -132,108 +161,159 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == 0) {
+    if (warp == kWarpProdA) {
         // ===================================================================== A producer
-        if (lane == 0) {
+        // (service warps run their loops warp-uniformly and predicate only the issue with elect_one: under a
+        //  `lane == 0` branch the compiler wraps every UTMALDG / UTCHMMA in an ELECT..BRA.U.ANY serialisation loop
+        //  with R2UR moves — measured 285 vs 195 cycles per MMA in csrc/mma_bench.cu)
+        {
             uint32_t slot = 0, phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord t = tile_coord(p, tile);
                 for (int ch = 0; ch < p.chunks; ++ch) {
-                    const int ii = ch / p.jc_chunks;
-                    const int jc0 = (ch - ii * p.jc_chunks) * kChunkK;
+                    const Chunk c = chunk_of(p, ch);
+                    const CUtensorMap* map = c.width == 64 ? &tmA64 : &tmA32;
+                    const uint32_t bytes = (uint32_t)(kSubH * p.ms + 2) * kSubW * c.width * 2;
                     for (int dwi = 0; dwi < 3; ++dwi) {
                         mbar_wait(smem_u32(&bars->a_empty[slot]), phase ^ 1);
-                        const uint32_t full = smem_u32(&bars->a_full[slot]);
-                        mbar_expect_tx(full, p.a_bytes);
-                        tma_load_5d(a_ring + slot * p.a_bytes, &tmA, full, jc0, t.w0 + dwi - 1, ii, t.h0 - 1, t.b);
+                        if (elect_one()) {
+                            const uint32_t full = smem_u32(&bars->a_full[slot]);
+                            mbar_expect_tx(full, bytes);
+                            tma_load_5d(a_ring + slot * p.a_bytes, map, full, c.jc0, t.w0 + dwi - 1, c.ii, t.h0 - 1, t.b);
+                        }
+                        __syncwarp();
                         if (++slot == (uint32_t)p.na) { slot = 0; phase ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == kWarpProdB) {
         // ===================================================================== weight producer
-        if (lane == 0) {
+        {
             uint32_t slot = 0, phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord t = tile_coord(p, tile);
                 for (int ch = 0; ch < p.chunks; ++ch) {
+                    const Chunk c = chunk_of(p, ch);
+                    const CUtensorMap* map = c.width == 64 ? &tmB64 : &tmB32;
+                    const uint32_t bytes = (uint32_t)p.block_n * c.width * 2;
+                    const int k0 = c.ii * p.cj + c.jc0;
                     for (int dwi = 0; dwi < 3; ++dwi) {
                         const int kw = 1 + (dwi - 1) * p.sign;
                         for (int dhi = 0; dhi < 3; ++dhi) {
                             const int kh = 1 + (dhi - 1) * p.sign;
                             mbar_wait(smem_u32(&bars->b_empty[slot]), phase ^ 1);
-                            const uint32_t full = smem_u32(&bars->b_full[slot]);
-                            mbar_expect_tx(full, p.b_bytes);
-                            tma_load_3d(b_ring + slot * p.b_bytes, &tmB, full, ch * kChunkK, t.n0, kh * 3 + kw);
+                            if (elect_one()) {
+                                const uint32_t full = smem_u32(&bars->b_full[slot]);
+                                mbar_expect_tx(full, bytes);
+                                tma_load_3d(b_ring + slot * p.b_bytes, map, full, k0, t.n0, kh * 3 + kw);
+                            }
+                            __syncwarp();
                             if (++slot == (uint32_t)p.nb) { slot = 0; phase ^= 1; }
                         }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================================================================== UMMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
-            uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0;
-            int it = 0;
-            const bool prof = p.prof != nullptr;
-            long long t_start = prof ? clk() : 0, w_a = 0, w_b = 0, w_t = 0, t0 = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const int buf = it % p.acc_bufs;
-                const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
-                if (prof) t0 = clk();
-                mbar_wait(smem_u32(&bars->tmem_empty[buf]), acc_phase ^ 1);
-                if (prof) w_t += clk() - t0;
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * p.ms * p.block_n;
-                uint32_t first = 1;
-                for (int ch = 0; ch < p.chunks; ++ch) {
-                    for (int dwi = 0; dwi < 3; ++dwi) {
-                        if (prof) t0 = clk();
-                        mbar_wait(smem_u32(&bars->a_full[aslot]), aphase);
-                        if (prof) w_a += clk() - t0;
-                        const uint32_t a_s = a_ring + aslot * p.a_bytes;
-                        for (int dhi = 0; dhi < 3; ++dhi) {
-                            if (prof) t0 = clk();
-                            mbar_wait(smem_u32(&bars->b_full[bslot]), bphase);
-                            if (prof) w_b += clk() - t0;
-                            tc_fence_after();
-                            const uint32_t b_s = b_ring + bslot * p.b_bytes;
+    } else if (warp >= kWarpMma0 && warp < kWarpMma0 + p.issuers) {
+        // ===================================================================== UMMA issuers
+        // A K-group = one A box (chunk, dw) and its three vertical taps: 3 * (width/16) * MS MMAs, then one burst
+        // of commits (3 weight slots + the A slot).  csrc/mma_bench.cu: a commit drains the issuing thread's MMAs
+        // (~600 cycles) before it can issue again, but two issuer warps overlap each other's drains
+        // (N=192: 1949 -> 3848 MAC/clk/SM).  So kIssuers warps take alternate K-groups of the SAME tile; the
+        // tensor pipe executes MMAs in arrival order, and the issuer of a tile's first (overwriting) group
+        // releases the others through `tile_started`.
+        const int me = warp - kWarpMma0;
+        const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
+        uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, gidx = 0;
+        int it = 0;
+        const bool prof = p.prof != nullptr && me == 0;
+        long long t_start = prof ? clk() : 0, w_a = 0, w_b = 0, w_t = 0, t0 = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it % p.acc_bufs;
+            const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
+            if (prof) t0 = clk();
+            mbar_wait(smem_u32(&bars->tmem_empty[buf]), acc_phase ^ 1);
+            if (prof) w_t += clk() - t0;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * p.ms * p.block_n;
+            bool first_group = true, joined = false;
+            for (int ch = 0; ch < p.chunks; ++ch) {
+                const Chunk c = chunk_of(p, ch);
+                const uint32_t row_b = c.width == 64 ? 1024u : 512u;   // bytes per image row of the box == SBO
+                const uint32_t lay = c.width == 64 ? SWZ_128B : SWZ_64B;
+                const int ksl = c.width / 16;
+                for (int dwi = 0; dwi < 3; ++dwi, ++gidx, first_group = false) {
+                    const bool mine = (gidx % (uint32_t)p.issuers) == (uint32_t)me;
+                    uint32_t b_s[3], b_bar[3];
+                    if (mine && !first_group && !joined) {
+                        mbar_wait(smem_u32(&bars->tile_started[buf]), acc_phase);
+                        joined = true;
+                    }
+                    // EVERY issuer observes EVERY phase of the full barriers, in order, even for groups it does
+                    // not own: a parity wait cannot tell phase k from phase k+2, so an issuer that skipped the other
+                    // issuer's groups could sail through a stale phase (guaranteed with a 3-slot ring).
+                    if (prof) t0 = clk();
+                    mbar_wait(smem_u32(&bars->a_full[aslot]), aphase);
+                    if (prof) { const long long t1 = clk(); w_a += t1 - t0; t0 = t1; }
+                    uint32_t bs = bslot, bp = bphase;
 #pragma unroll
-                            for (int k = 0; k < kChunkK / 16; ++k) {
-                                const uint64_t bdesc = make_smem_desc(b_s + k * 32, 16, 512, SWZ_64B);
-                                for (int ms = 0; ms < p.ms; ++ms) {
-                                    // rows of sub-tile ms for vertical tap dh: box rows (dhi + 16*ms) ...
-                                    const uint64_t adesc =
-                                        make_smem_desc(a_s + (dhi + kSubH * ms) * kRowBytes + k * 32, 16, 512, SWZ_64B);
-                                    umma_bf16(d_tmem + ms * p.block_n, adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
+                    for (int dhi = 0; dhi < 3; ++dhi) {
+                        mbar_wait(smem_u32(&bars->b_full[bs]), bp);
+                        b_s[dhi] = b_ring + bs * p.b_bytes;
+                        b_bar[dhi] = smem_u32(&bars->b_empty[bs]);
+                        if (++bs == (uint32_t)p.nb) { bs = 0; bp ^= 1; }
+                    }
+                    if (mine) {
+                        if (prof) w_b += clk() - t0;
+                        tc_fence_after();
+                        const uint32_t a_s = a_ring + aslot * p.a_bytes;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int dhi = 0; dhi < 3; ++dhi) {
+                                for (int k = 0; k < ksl; ++k) {
+                                    const uint64_t bdesc = make_smem_desc(b_s[dhi] + k * 32, 16, row_b, lay);
+                                    for (int ms = 0; ms < p.ms; ++ms) {
+                                        // rows of sub-tile ms for vertical tap dh: box rows (dhi + 16*ms) ...
+                                        const uint64_t adesc =
+                                            make_smem_desc(a_s + (dhi + kSubH * ms) * row_b + k * 32, 16, row_b, lay);
+                                        umma_bf16(d_tmem + ms * p.block_n, adesc, bdesc, idesc,
+                                                  (first_group && dhi == 0 && k == 0) ? 0u : 1u);
+                                    }
                                 }
                             }
-                            first = 0;
-                            umma_commit(smem_u32(&bars->b_empty[bslot]));
-                            if (++bslot == (uint32_t)p.nb) { bslot = 0; bphase ^= 1; }
+                            if (first_group) mbar_arrive(smem_u32(&bars->tile_started[buf]));
+#pragma unroll
+                            for (int dhi = 0; dhi < 3; ++dhi) umma_commit(b_bar[dhi]);
+                            umma_commit(smem_u32(&bars->a_empty[aslot]));
                         }
-                        umma_commit(smem_u32(&bars->a_empty[aslot]));
-                        if (++aslot == (uint32_t)p.na) { aslot = 0; aphase ^= 1; }
+                        __syncwarp();
+                        if (first_group) joined = true;
                     }
+                    bslot = bs;
+                    bphase = bp;
+                    if (++aslot == (uint32_t)p.na) { aslot = 0; aphase ^= 1; }
                 }
-                umma_commit(smem_u32(&bars->tmem_full[buf]));
             }
-            if (prof) {
-                long long* o = p.prof + (size_t)blockIdx.x * 8;
-                o[0] = clk() - t_start; o[1] = w_a; o[2] = w_b; o[3] = w_t; o[7] = it;
-            }
+            if (elect_one()) umma_commit(smem_u32(&bars->tmem_full[buf]));   // one arrival per issuer
+            __syncwarp();
         }
-    } else {
-        // ===================================================================== epilogue (warps 3..6)
+        if (prof && lane == 0) {
+            long long* o = p.prof + (size_t)blockIdx.x * 8;
+            o[0] = clk() - t_start; o[1] = w_a; o[2] = w_b; o[3] = w_t; o[7] = it;
+        }
+    } else if (warp < kEpiWarps) {
+        // ===================================================================== epilogue (warps 0..7)
+        // Two warps per TMEM lane quarter: warp half 0 handles columns [0,32) of every 64-column group,
+        // half 1 columns [32,64).  One iteration = 64 accumulator columns -> one 128-byte-row store tile
+        // (SWIZZLE_128B) when the output channel range allows it, otherwise two 64-byte-row tiles.
+        const int ew = warp;
         const int q = warp & 3;             // TMEM lane quarter this warp may touch
+        const int half = ew >> 2;           // warps 0..3 -> 0, warps 4..7 -> 1
         const int row = q * 32 + lane;      // accumulator row == pixel inside the 16 x 8 sub-tile
         const int hl = row >> 3, wl = row & 7;
-        const bool store_thread = (warp == 3 && lane == 0);
-        const uint32_t swz = (uint32_t)((row >> 1) & 3);
-        uint32_t chunk_ctr = 0;
+        const bool store_thread = (ew == 0 && lane == 0);
+        uint32_t iter_ctr = 0;
         int it = 0;
         const bool prof = p.prof != nullptr && store_thread;
         long long e_full = 0, e_store = 0, e_busy = 0, t0 = 0, t1 = 0;
@@ -245,85 +325,115 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(smem_u32(&bars->tmem_full[buf]), acc_phase);
             if (prof) { t1 = clk(); e_full += t1 - t0; }
             tc_fence_after();
-            const int nchunks = p.block_n / 32;
+            const int ngroups = (p.block_n + 63) / 64;
             for (int ms = 0; ms < p.ms; ++ms) {
                 const int hs0 = t.h0 + ms * kSubH;
                 if (hs0 >= p.H) break;      // sub-tile entirely below the image (uniform across the CTA)
-                for (int c = 0; c < nchunks; ++c) {
-                    const int n = t.n0 + c * 32;
-                    if (n >= p.n_total) break;
-                    const uint32_t sbuf = chunk_ctr & 1u;
-                    ++chunk_ctr;
+                for (int g = 0; g < ngroups; ++g) {
+                    const int n_g = t.n0 + g * 64;              // first output channel of the group
+                    if (n_g >= p.n_total) break;
+                    const int col = g * 64 + half * 32;         // this warp's columns inside the tile
+                    const int n = t.n0 + col;
+                    const bool valid = col < p.block_n && n < p.n_total;
+                    // wide store: all 64 channels valid, same shuffle row i, 64-aligned inside it
+                    const int oi = n_g / p.out_jc;
+                    const int ojc = n_g - oi * p.out_jc;
+                    const bool wide = (g * 64 + 64 <= p.block_n) && (n_g + 64 <= p.n_total) && (ojc % 64 == 0) &&
+                                      (ojc + 64 <= p.out_jc);
+                    const uint32_t sbuf = iter_ctr & 1u;
+                    ++iter_ctr;
                     if (prof) t0 = clk();
                     if (store_thread) tma_store_wait_read<1>();
                     if (prof) e_store += clk() - t0;
-                    named_bar_sync(1, 128);
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.ms + ms) * p.block_n + c * 32, r);
-                    tmem_ld_wait();
+                    named_bar_sync(1, kEpiThreads);
                     const uint32_t ybuf = staging + sbuf * 2 * kStageOutBytes;
                     const uint32_t dbuf = ybuf + kStageOutBytes;
-                    if (p.mode == ONR_CONV_DGRAD) {
-                        const int h = hs0 + hl, w = t.w0 + wl;
-                        uint4 dv[4];
-                        if (h < p.H && w < p.W) {
-                            const uint4* dp = reinterpret_cast<const uint4*>(
-                                p.dmul + ((size_t)(t.b * p.H + h) * p.W + w) * p.n_total + n);
+                    if (valid) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.ms + ms) * p.block_n + col, r);
+                        tmem_ld_wait();
+                        // staging address of this thread's 16-byte piece j (0..3) of its 32 channels
+                        //   wide  : [128 rows][128 B], SWIZZLE_128B: piece (4*half + j) ^ (row & 7)
+                        //   narrow: tile `half` of [128 rows][64 B], SWIZZLE_64B: piece j ^ ((row >> 1) & 3)
+                        const uint32_t rbase = wide ? row * 128u : half * (kStageOutBytes / 2) + row * 64u;
+                        const uint32_t sx = wide ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+                        const uint32_t jofs = wide ? half * 4u : 0u;
+                        if (p.mode == ONR_CONV_DGRAD) {
+                            const int h = hs0 + hl, w = t.w0 + wl;
+                            uint4 dv[4];
+                            if (h < p.H && w < p.W) {
+                                const uint4* dp = reinterpret_cast<const uint4*>(
+                                    p.dmul + ((size_t)(t.b * p.H + h) * p.W + w) * p.n_total + n);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dv[j] = __ldg(dp + j);
-                        } else {
+                                for (int j = 0; j < 4; ++j) dv[j] = __ldg(dp + j);
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dv[j] = make_uint4(0, 0, 0, 0);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t dw4[4] = {dv[j].x, dv[j].y, dv[j].z, dv[j].w};
-                            uint32_t o[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float a0 = __uint_as_float(r[j * 8 + e * 2]) * bf16_lo(dw4[e]);
-                                const float a1 = __uint_as_float(r[j * 8 + e * 2 + 1]) * bf16_hi(dw4[e]);
-                                o[e] = pack_bf16x2(a0, a1);
+                                for (int j = 0; j < 4; ++j) dv[j] = make_uint4(0, 0, 0, 0);
                             }
-                            const uint32_t addr = ybuf + row * 64 + ((j ^ swz) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(o[0]),
-                                         "r"(o[1]), "r"(o[2]), "r"(o[3])
-                                         : "memory");
-                        }
-                    } else {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b0 = __ldg(bp + j * 2), b1 = __ldg(bp + j * 2 + 1);
-                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                            float yv[8], dv[8];
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t dw4[4] = {dv[j].x, dv[j].y, dv[j].z, dv[j].w};
+                                uint32_t o[4];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float z = __uint_as_float(r[j * 8 + e]) + bb[e];
-                                const float sg = fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
-                                const float y = z * sg;
-                                yv[e] = y;
-                                dv[e] = fmaf(y, 1.0f - sg, sg);
-                            }
-                            const uint32_t off = row * 64 + ((j ^ swz) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(ybuf + off),
-                                         "r"(pack_bf16x2(yv[0], yv[1])), "r"(pack_bf16x2(yv[2], yv[3])),
-                                         "r"(pack_bf16x2(yv[4], yv[5])), "r"(pack_bf16x2(yv[6], yv[7]))
-                                         : "memory");
-                            if (p.mode == ONR_CONV_FPROP_TRAIN)
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dbuf + off),
-                                             "r"(pack_bf16x2(dv[0], dv[1])), "r"(pack_bf16x2(dv[2], dv[3])),
-                                             "r"(pack_bf16x2(dv[4], dv[5])), "r"(pack_bf16x2(dv[6], dv[7]))
+                                for (int e = 0; e < 4; ++e) {
+                                    const float a0 = __uint_as_float(r[j * 8 + e * 2]) * bf16_lo(dw4[e]);
+                                    const float a1 = __uint_as_float(r[j * 8 + e * 2 + 1]) * bf16_hi(dw4[e]);
+                                    o[e] = pack_bf16x2(a0, a1);
+                                }
+                                const uint32_t addr = ybuf + rbase + (((jofs + j) ^ sx) << 4);
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(o[0]),
+                                             "r"(o[1]), "r"(o[2]), "r"(o[3])
                                              : "memory");
+                            }
+                        } else {
+                            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 b0 = __ldg(bp + j * 2), b1 = __ldg(bp + j * 2 + 1);
+                                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                                float yv[8], dv[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float z = __uint_as_float(r[j * 8 + e]) + bb[e];
+                                    const float sg = fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
+                                    const float y = z * sg;
+                                    yv[e] = y;
+                                    dv[e] = fmaf(y, 1.0f - sg, sg);
+                                }
+                                const uint32_t off = rbase + (((jofs + j) ^ sx) << 4);
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(ybuf + off),
+                                             "r"(pack_bf16x2(yv[0], yv[1])), "r"(pack_bf16x2(yv[2], yv[3])),
+                                             "r"(pack_bf16x2(yv[4], yv[5])), "r"(pack_bf16x2(yv[6], yv[7]))
+                                             : "memory");
+                                if (p.mode == ONR_CONV_FPROP_TRAIN)
+                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dbuf + off),
+                                                 "r"(pack_bf16x2(dv[0], dv[1])), "r"(pack_bf16x2(dv[2], dv[3])),
+                                                 "r"(pack_bf16x2(dv[4], dv[5])), "r"(pack_bf16x2(dv[6], dv[7]))
+                                                 : "memory");
+                            }
                         }
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(2, 128);
+                    named_bar_sync(2, kEpiThreads);
                     if (store_thread) {
-                        const int oi = n / p.out_jc;
-                        const int ojc = n - oi * p.out_jc;
-                        tma_store_5d(&tmY, ybuf, ojc, t.w0, oi, hs0, t.b);
-                        if (p.mode == ONR_CONV_FPROP_TRAIN) tma_store_5d(&tmD, dbuf, ojc, t.w0, oi, hs0, t.b);
+                        const bool train = p.mode == ONR_CONV_FPROP_TRAIN;
+                        if (wide) {
+                            tma_store_5d(&tmY64, ybuf, ojc, t.w0, oi, hs0, t.b);
+                            if (train) tma_store_5d(&tmD64, dbuf, ojc, t.w0, oi, hs0, t.b);
+                        } else {
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int colh = g * 64 + hh * 32;
+                                const int nh = t.n0 + colh;
+                                if (colh < p.block_n && nh < p.n_total) {
+                                    const int oih = nh / p.out_jc;
+                                    const int ojh = nh - oih * p.out_jc;
+                                    tma_store_5d(&tmY32, ybuf + hh * (kStageOutBytes / 2), ojh, t.w0, oih, hs0, t.b);
+                                    if (train)
+                                        tma_store_5d(&tmD32, dbuf + hh * (kStageOutBytes / 2), ojh, t.w0, oih, hs0, t.b);
+                                }
+                            }
+                        }
                         tma_store_commit();
                     }
                 }
@@ -341,7 +451,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kWarpMma) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -351,7 +461,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // ------------------------------------------------------------------------------------------- host
 struct onr_conv_plan {
-    CUtensorMap tmA, tmB, tmY, tmD;
+    CUtensorMap tmA64, tmA32, tmB64, tmB32, tmY64, tmY32, tmD64, tmD32;
     onr::ConvParams p;
     int grid;
     size_t smem;
@@ -359,15 +469,24 @@ struct onr_conv_plan {
 
 extern "C" {
 
-// N tiling rule shared with the weight packer: block_n <= 256 (one UMMA per K slice), multiple of 32,
-// chosen to minimise zero padding.
+// N tiling rule shared with the weight packer: block_n is a multiple of 32, <= 256 (one UMMA per K slice and room
+// for two accumulator buffers), chosen to minimise operand bytes per useful MAC:
+//   bytes/tile ~ 3 * (16*ms + 2) * 8  (A box rows per 32 channels)  +  9 * block_n  (weight rows)
+//   MACs/tile  ~ ms * 128 * block_n * 9,   ms = min(4, 256 / block_n) sub-tiles,   x padding waste block_n*n_tiles/N.
+// (384 -> 3 x 128 with 2 sub-tiles; 96 -> 96 with 2 sub-tiles; 800 -> 7 x 128.)
 int onr_conv_tile_n(int n_total, int* block_n, int* n_tiles) {
     ONR_REQUIRE(n_total > 0 && n_total % 32 == 0, "n_total must be a positive multiple of 32");
-    const int nt0 = (n_total + onr::kMaxBlockN - 1) / onr::kMaxBlockN;
-    int best_nt = nt0, best_bn = ((n_total + nt0 - 1) / nt0 + 31) / 32 * 32;
-    for (int nt = nt0; nt <= nt0 + 3; ++nt) {
-        const int bn = ((n_total + nt - 1) / nt + 31) / 32 * 32;
-        if (bn * nt < best_bn * best_nt) { best_nt = nt; best_bn = bn; }
+    double best = 1e300;
+    int best_bn = 32, best_nt = n_total / 32;
+    for (int bn = 32; bn <= onr::kMaxBlockN; bn += 32) {
+        const int nt = (n_total + bn - 1) / bn;
+        if (nt > 1 && bn < 64) continue;                      // tiny N tiles only for tiny N
+        int ms = 256 / bn;
+        if (ms > onr::kMaxMS) ms = onr::kMaxMS;
+        const double bytes = 3.0 * (16 * ms + 2) * 8 + 9.0 * bn;
+        const double macs = (double)ms * 128 * bn * 9;
+        const double cost = bytes / macs * ((double)bn * nt / n_total);
+        if (cost < best * 0.9999) { best = cost; best_bn = bn; best_nt = nt; }
     }
     if (block_n) *block_n = best_bn;
     if (n_tiles) *n_tiles = best_nt;
@@ -395,7 +514,8 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     p.block_n = block_n;
     p.n_tiles = n_tiles;
     // sub-tiles per CTA tile: as many as TMEM allows, but keep >= 2 tiles per SM when the layer is large enough
-    int ms_max = 512 / block_n;
+    int ms_max = 256 / block_n;          // always leave room for two accumulator buffers
+    if (ms_max < 1) ms_max = 1;
     if (ms_max > kMaxMS) ms_max = kMaxMS;
     const int k_tap0 = d->a_s * d->a_s * d->a_cp;
     int ms = 1;
@@ -405,7 +525,7 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
         for (int m = 1; m <= ms_max; ++m) {
             const long long tiles = (long long)d->B * ceil_div(d->H, kSubH * m) * ceil_div(d->W, kSubW) * n_tiles;
             const double waves = (double)((tiles + num_sms() - 1) / num_sms());
-            const double bytes = (double)(k_tap0 / kChunkK) * (3.0 * (kSubH * m + 2) * kRowBytes + 9.0 * block_n * 64);
+            const double bytes = (double)(k_tap0 / 32) * (3.0 * (kSubH * m + 2) * kSubW * 64 + 9.0 * block_n * 64);
             const double cost = waves * bytes;
             if (cost < best * 0.999) { best = cost; ms = m; }
         }
@@ -417,39 +537,53 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     p.tiles_h = ceil_div(d->H, kSubH * ms);
     p.total_tiles = d->B * p.tiles_h * p.tiles_w * n_tiles;
     const int k_tap = d->a_s * d->a_s * d->a_cp;
-    p.chunks = k_tap / kChunkK;
-    p.jc_chunks = d->a_s * d->a_cp / kChunkK;
+    p.cj = d->a_s * d->a_cp;                      // channels per shuffle row i of the A view
+    p.n64 = p.cj / 64;
+    p.cpi = p.n64 + ((p.cj % 64) ? 1 : 0);
+    p.chunks = d->a_s * p.cpi;
     p.sign = d->kind == ONR_CONV_DGRAD ? -1 : 1;
     p.n_total = d->n_total;
-    p.acc_bufs = (2 * ms * block_n <= 512) ? 2 : 1;
+    p.acc_bufs = 2;
+    p.issuers = kMaxIssuers;
+    if (const char* e = getenv("ONR_CONV_ISSUERS")) {     // experiments only
+        const int v = atoi(e);
+        if (v >= 1 && v <= kMaxIssuers) p.issuers = v;
+    }
     p.mode = d->kind;
     p.out_jc = d->out_s * d->out_cp;
     p.bias = d->bias_p;
     p.dmul = reinterpret_cast<const __nv_bfloat16*>(d->dmul);
     p.prof = nullptr;
     const int box_h = kSubH * ms + 2;
-    p.a_bytes = box_h * kRowBytes;                      // multiple of 512
+    const int wmax = p.n64 > 0 ? 64 : 32;               // widest chunk this plan uses
+    p.a_bytes = box_h * kSubW * wmax * 2;               // multiple of 1024 (64-wide) / 512 (32-wide)
     p.a_bytes = (p.a_bytes + 1023) / 1024 * 1024;       // keep every slot 1024-aligned
-    p.b_bytes = block_n * 64;                           // multiple of 2048
+    p.b_bytes = block_n * wmax * 2;                     // multiple of 2048
     // ring depths: ~96 KB of A boxes at most, the rest for weight tiles
     const int budget = kMaxDynSmem - 1024 - 4 * kStageOutBytes - (int)sizeof(SmemBarriers) - 1024;
+    // one A box feeds three weight tiles, so two or three A slots are enough; weight tiles get the rest
     int na = 3;
-    while (na > 2 && na * p.a_bytes > budget / 2) --na;
+    while (na > 2 && (na * p.a_bytes > budget / 2 || (budget - na * p.a_bytes) / p.b_bytes < 6)) --na;
     int nb = (budget - na * p.a_bytes) / p.b_bytes;
     if (nb > kMaxRing) nb = kMaxRing;
-    ONR_REQUIRE(nb >= 2, "conv plan: shared memory too small for block_n %d ms %d", block_n, ms);
-    // spend what is left on deeper A ring
-    while (na < kMaxRing && (na + 1) * p.a_bytes + nb * p.b_bytes <= budget && na < 4) ++na;
+    ONR_REQUIRE(nb >= 3, "conv plan: shared memory too small for block_n %d ms %d", block_n, ms);
+    // spend what is left on a deeper A ring
+    while (na < 4 && (na + 1) * p.a_bytes + nb * p.b_bytes <= budget) ++na;
     p.na = na;
     p.nb = nb;
     pl->smem = 1024 + (size_t)na * p.a_bytes + (size_t)nb * p.b_bytes + 4 * kStageOutBytes + sizeof(SmemBarriers);
     pl->grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    int rc = make_act_tmap(&pl->tmA, d->a, d->B, d->H, d->W, d->a_cp, d->a_s, kSubW, box_h);
-    if (!rc) rc = make_weight_tmap(&pl->tmB, d->w, 9, d->n_rows, k_tap, block_n);
-    if (!rc) rc = make_act_tmap(&pl->tmY, d->out, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH);
-    if (!rc)
-        rc = make_act_tmap(&pl->tmD, d->kind == ONR_CONV_FPROP_TRAIN ? d->out_d : d->out, d->B, d->H, d->W,
-                           d->out_cp, d->out_s, kSubW, kSubH);
+    // 64-channel maps only exist when the channel extent allows them; otherwise they alias the 32-wide ones
+    const int a64 = p.cj >= 64 ? 64 : 32, o64 = p.out_jc >= 64 ? 64 : 32, b64 = k_tap >= 64 ? 64 : 32;
+    const void* outd = d->kind == ONR_CONV_FPROP_TRAIN ? d->out_d : d->out;
+    int rc = make_act_tmap(&pl->tmA64, d->a, d->B, d->H, d->W, d->a_cp, d->a_s, kSubW, box_h, a64);
+    if (!rc) rc = make_act_tmap(&pl->tmA32, d->a, d->B, d->H, d->W, d->a_cp, d->a_s, kSubW, box_h, 32);
+    if (!rc) rc = make_weight_tmap(&pl->tmB64, d->w, 9, d->n_rows, k_tap, block_n, b64);
+    if (!rc) rc = make_weight_tmap(&pl->tmB32, d->w, 9, d->n_rows, k_tap, block_n, 32);
+    if (!rc) rc = make_act_tmap(&pl->tmY64, d->out, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, o64);
+    if (!rc) rc = make_act_tmap(&pl->tmY32, d->out, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, 32);
+    if (!rc) rc = make_act_tmap(&pl->tmD64, outd, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, o64);
+    if (!rc) rc = make_act_tmap(&pl->tmD32, outd, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, 32);
     if (rc) { delete pl; return rc; }
     // The attribute is per function, not per plan: raise it once to the opt-in maximum (227 KB on sm_100).
     static bool attr_set = false;
@@ -475,8 +609,8 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
 int onr_conv_plan_run(const onr_conv_plan* pl, void* stream) {
     using namespace onr;
     ONR_REQUIRE(pl != nullptr, "null plan");
-    conv_igemm_kernel<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmY,
-                                                                             pl->tmD, pl->p);
+    conv_igemm_kernel<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(
+        pl->tmA64, pl->tmA32, pl->tmB64, pl->tmB32, pl->tmY64, pl->tmY32, pl->tmD64, pl->tmD32, pl->p);
     ONR_LAUNCH_CHECK();
     return 0;
 }

@@ -37,34 +37,37 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_act_tmap(CUtensorMap* map, const void* ptr, int B, int H, int W, int Cp, int s, int box_w,
-                  int box_h) {
+                  int box_h, int inner) {
     EncodeTiledFn enc = get_encode();
     ONR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
-    ONR_REQUIRE(Cp % 32 == 0 && s >= 1 && box_w <= 256 && box_h <= 256, "make_act_tmap: bad shape");
+    ONR_REQUIRE(Cp % 32 == 0 && s >= 1 && box_w <= 256 && box_h <= 256 && (inner == 32 || inner == 64),
+                "make_act_tmap: bad shape");
     const cuuint64_t Ws = (cuuint64_t)W * s;
     cuuint64_t dims[5] = {(cuuint64_t)s * Cp, (cuuint64_t)W, (cuuint64_t)s, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[4] = {(cuuint64_t)2 * s * Cp, (cuuint64_t)2 * Ws * Cp, (cuuint64_t)2 * s * Ws * Cp,
                              (cuuint64_t)2 * s * H * Ws * Cp};
-    cuuint32_t box[5] = {32, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, 1};
+    cuuint32_t box[5] = {(cuuint32_t)inner, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ONR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act) failed: %d (B%d H%d W%d Cp%d s%d)", (int)r,
                 B, H, W, Cp, s);
     return 0;
 }
 
-int make_weight_tmap(CUtensorMap* map, const void* ptr, int taps, int rows, int k, int box_rows) {
+int make_weight_tmap(CUtensorMap* map, const void* ptr, int taps, int rows, int k, int box_rows, int inner) {
     EncodeTiledFn enc = get_encode();
     ONR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
-    ONR_REQUIRE(k % 32 == 0 && box_rows <= 256, "make_weight_tmap: bad shape");
+    ONR_REQUIRE(k % 32 == 0 && box_rows <= 256 && (inner == 32 || inner == 64), "make_weight_tmap: bad shape");
     cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)2 * k, (cuuint64_t)2 * k * rows};
-    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)inner, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ONR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d", (int)r);
     return 0;

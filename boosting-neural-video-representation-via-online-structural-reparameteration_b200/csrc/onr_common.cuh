@@ -61,10 +61,11 @@ static inline int pad32(int c) { return (c + 31) / 32 * 32; }
 // 5-D TMA view of an NHWC bf16 activation [B][H*s][W*s][Cp] as the pre-PixelShuffle tensor
 // (jc = j*Cp + c  |  w  |  i  |  h  |  b); s = 1 gives the plain NHWC tensor.
 // box = {32 channels (64 B, SWIZZLE_64B), box_w, 1, box_h, 1}.
+// box = {inner channels (32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B), box_w, 1, box_h, 1}.
 int make_act_tmap(CUtensorMap* map, const void* ptr, int B, int H, int W, int Cp, int s, int box_w,
-                  int box_h);
-// 3-D TMA view of packed weights [taps][rows][k] bf16; box = {32, box_rows, 1}.
-int make_weight_tmap(CUtensorMap* map, const void* ptr, int taps, int rows, int k, int box_rows);
+                  int box_h, int inner = 32);
+// 3-D TMA view of packed weights [taps][rows][k] bf16; box = {inner, box_rows, 1}.
+int make_weight_tmap(CUtensorMap* map, const void* ptr, int taps, int rows, int k, int box_rows, int inner = 32);
 
 // ----------------------------------------------------------------------------- device helpers
 __device__ __forceinline__ float warp_sum(float v) {

@@ -271,7 +271,40 @@ static int run_wgrad(const Shape& sh, int reps, bool check) {
     return ok ? 0 : 1;
 }
 
+static int run_mma_bench() {
+    const int grid = 148;
+    long long* out;
+    CK(cudaMalloc(&out, grid * sizeof(long long)));
+    const char* lname[4] = {"K-major SW128", "K-major SW64", "MN-major SW64", "MN-major SW128"};
+    printf("%-15s %4s %4s %6s %5s %7s | cycles/MMA  ideal  MAC/clk/SM\n", "layout", "N", "nacc", "percmt", "depth", "uniform");
+    const int Ns[] = {96, 192, 256};
+    const int a_stride = 16384;
+    for (int layout = 0; layout < 1; ++layout)
+        for (int n : Ns)
+            for (int nacc : {1})
+                for (int per_commit : {2, 4, 8, 16, 64})
+                    for (int depth : {1, 6})
+                        for (int uniform : {1, 2}) {
+                            if (uniform == 2 && n > 256) continue;
+                            const int iters = 2048 / per_commit;
+                            OK(onr_mma_bench(n, nacc, per_commit, iters, depth, layout, a_stride, uniform, out, grid, 0));
+                            CK(cudaDeviceSynchronize());
+                            std::vector<long long> h(grid);
+                            CK(cudaMemcpy(h.data(), out, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+                            double avg = 0;
+                            for (long long v : h) avg += (double)v / grid;
+                            const double per = avg / 2048.0;
+                            printf("%-15s %4d %4d %6d %5d %7d | %9.1f  %5.0f  %8.0f\n", lname[layout], n, nacc, per_commit,
+                                   depth, uniform, per, 128.0 * n / 256.0, 128.0 * n * 16.0 / per * (uniform == 2 ? 2 : 1));
+                        }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && !strcmp(argv[1], "mmabench")) {
+        OK(onr_check_device());
+        return run_mma_bench();
+    }
     if (argc < 3) {
         printf("usage: %s <fprop|infer|dgrad|wgrad> <shape> [reps] [nocheck]\nshapes:", argv[0]);
         for (const Shape& s : kShapes) printf(" %s", s.name);

@@ -21,7 +21,9 @@ namespace onr {
 constexpr int kWgPx = 64;          // pixels (reduction elements) per pipeline stage
 constexpr int kWgBox = kWgPx * 64; // bytes of one 32-channel box
 constexpr int kWgStages = 6;
+// warps 0..3 = epilogue, warp 4 = TMA producer, warp 5 = UMMA issuer (highest id: never starved by the others)
 constexpr int kWgThreads = 192;
+constexpr int kWgWarpProd = 4, kWgWarpMma = 5;
 constexpr int kWgRowsPerUnit = 24;
 
 struct WgradParams {
@@ -62,11 +64,11 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
         mbar_init(smem_u32(&bars->acc_full), 1);
         fence_mbar_init();
     }
-    if (warp == 0 && lane == 0) {
+    if (warp == kWgWarpProd && lane == 0) {
         tma_prefetch_desc(&tmDz);
         tma_prefetch_desc(&tmX);
     }
-    if (warp == 1) {
+    if (warp == kWgWarpMma) {
         tmem_alloc(smem_u32(&bars->tmem_base), 512);
         tmem_relinquish();
     }
@@ -75,8 +77,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == 0) {
-        if (lane == 0) {
+    if (warp == kWgWarpProd) {
+        {   // warp-uniform loop, issue predicated by elect_one (see conv_igemm.cu)
             uint32_t g = 0;
             for (int u = u0; u < u1; ++u) {
                 const int hu = u % p.hunits;
@@ -89,26 +91,29 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
                     const uint32_t stage = g % kWgStages;
                     const uint32_t phase = (g / kWgStages) & 1u;
                     mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
-                    const uint32_t full = smem_u32(&bars->full[stage]);
-                    const uint32_t dz_s = smem_base + stage * stage_bytes;
-                    const uint32_t x_s = dz_s + 4 * kWgBox;
-                    const bool with_x = r >= r0;
-                    mbar_expect_tx(full, (with_x ? (4 + p.xb) : 4) * kWgBox);
-                    // dZ row r+1, four 32-channel boxes of this CTA's 128-channel n tile
-                    for (int qb = 0; qb < 4; ++qb) {
-                        const int qn = n_tile * 4 + qb;  // 32-channel chunk of n'
-                        const int ii = qn / p.jc_chunks;
-                        const int jc0 = (qn - ii * p.jc_chunks) * 32;
-                        tma_load_5d(dz_s + qb * kWgBox, &tmDz, full, jc0, wbase, ii, r + 1, b);
+                    if (elect_one()) {
+                        const uint32_t full = smem_u32(&bars->full[stage]);
+                        const uint32_t dz_s = smem_base + stage * stage_bytes;
+                        const uint32_t x_s = dz_s + 4 * kWgBox;
+                        const bool with_x = r >= r0;
+                        mbar_expect_tx(full, (with_x ? (4 + p.xb) : 4) * kWgBox);
+                        // dZ row r+1, four 32-channel boxes of this CTA's 128-channel n tile
+                        for (int qb = 0; qb < 4; ++qb) {
+                            const int qn = n_tile * 4 + qb;  // 32-channel chunk of n'
+                            const int ii = qn / p.jc_chunks;
+                            const int jc0 = (qn - ii * p.jc_chunks) * 32;
+                            tma_load_5d(dz_s + qb * kWgBox, &tmDz, full, jc0, wbase, ii, r + 1, b);
+                        }
+                        if (with_x)
+                            for (int xb = 0; xb < p.xb; ++xb)
+                                tma_load_5d(x_s + xb * kWgBox, &tmX, full, xb * 32, wbase + kw - 1, 0, r, b);
                     }
-                    if (with_x)
-                        for (int xb = 0; xb < p.xb; ++xb)
-                            tma_load_5d(x_s + xb * kWgBox, &tmX, full, xb * 32, wbase + kw - 1, 0, r, b);
+                    __syncwarp();
                 }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
+    } else if (warp == kWgWarpMma) {
+        {
             const uint32_t idesc = make_idesc_bf16(128, p.x_cp, 1, 1);
             uint32_t g = 0;
             uint32_t started = 0;  // bit kh set once acc[kh] holds data
@@ -121,7 +126,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
                     const uint32_t phase = (g / kWgStages) & 1u;
                     mbar_wait(smem_u32(&bars->full[stage]), phase);
                     tc_fence_after();
-                    if (r >= r0) {
+                    if (elect_one()) {
+                      if (r >= r0) {
                         const uint32_t x_s = smem_base + stage * stage_bytes + 4 * kWgBox;
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
@@ -134,13 +140,16 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
                                 umma_bf16(tmem_base + kh * p.x_cp, adesc, bdesc, idesc,
                                           ((started >> kh) & 1u) | (kk != 0));
                             }
-                            started |= 1u << kh;
                         }
+                      }
+                      if (g >= 2) umma_commit(smem_u32(&bars->empty[(g - 2) % kWgStages]));
                     }
-                    if (g >= 2) umma_commit(smem_u32(&bars->empty[(g - 2) % kWgStages]));
+                    __syncwarp();
+                    if (r >= r0) started = 7u;
                 }
             }
-            umma_commit(smem_u32(&bars->acc_full));
+            if (elect_one()) umma_commit(smem_u32(&bars->acc_full));
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -169,7 +178,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kWgWarpMma) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

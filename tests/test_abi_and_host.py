@@ -26,11 +26,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_tile_n_rule():
     from orepnerv.engine import conv_tile_n
-    assert conv_tile_n(384) == (192, 2)
-    assert conv_tile_n(96) == (96, 1)
-    assert conv_tile_n(800) == (160, 5)
-    assert conv_tile_n(864) == (224, 4)
-    assert conv_tile_n(3200) == (256, 13)
+    for n in (32, 96, 128, 384, 800, 864, 3200):
+        bn, nt = conv_tile_n(n)
+        assert bn % 32 == 0 and bn <= 256 and bn * nt >= n and bn * (nt - 1) < n
+    assert conv_tile_n(384) == (128, 3)         # block 1-4 forward: 2 sub-tiles share each weight tile
+    assert conv_tile_n(96) == (96, 1)           # dgrad of those blocks
+    assert conv_tile_n(32) == (32, 1)
     lib = _lib.load()
     assert lib.onr_conv_tile_n(33, None, None) < 0        # not a multiple of 32 -> error code, message set
     assert b"multiple of 32" in lib.onr_last_error()
