@@ -46,45 +46,64 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region, in-process through NVML (nvidia_ml_py).
+    (An external `nvidia-smi -lms 100` poller next to the persistent tcgen05 kernels coincided with GPU-side hangs
+    on this driver — see DESIGN.md section 6 — so nothing is spawned here.)"""
 
-    def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, period_s=0.25):
+        self.gpu, self.period, self.rows, self.thread = gpu_index, period_s, [], None
+        self._stop = threading.Event()
+        self.mode = os.environ.get("ONR_BENCH_SAMPLER", "nvml")      # nvml | smi | off
+
+    def _nvml_loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            while not self._stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(mx), [n for n, bit in bits.items() if r & bit]))
+                self._stop.wait(self.period)
+        except Exception as exc:                                       # noqa: BLE001
+            self.rows.append((None, None, [f"nvml unavailable: {exc}"]))
+
+    def _smi_loop(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                c = [x.strip() for x in out.strip().split(",")]
+                self.rows.append((float(c[0]), float(c[1]), [n for n, v in zip(names, c[2:6]) if v.lower() == "active"]))
+            except Exception as exc:                                   # noqa: BLE001
+                self.rows.append((None, None, [f"nvidia-smi unavailable: {exc}"]))
+            self._stop.wait(max(self.period, 0.5))
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        if self.mode == "off":
+            return
+        self.thread = threading.Thread(target=self._smi_loop if self.mode == "smi" else self._nvml_loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
-        # idle samples before the first kernel pull the median down; keep the busy half
-        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler off"], "samples": 0}
+        self._stop.set()
+        self.thread.join(timeout=3)
+        sm = sorted(r[0] for r in self.rows if r[0] is not None)
+        mx = [r[1] for r in self.rows if r[1] is not None]
+        reasons = sorted({x for r in self.rows for x in r[2]})
+        busy = sm[len(sm) // 2:]           # idle samples before the first kernel pull the median down
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.mode}
 
 
 def make_args(world):
@@ -316,7 +335,15 @@ def run_ours(opts):
         dist.destroy_process_group()
 
 
+def _arm_watchdog(seconds):
+    """A wedged GPU wait must not hang the harness: dump every Python stack and exit non-zero."""
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(seconds, exit=True)
+
+
 def main():
+    _arm_watchdog(int(os.environ.get("ONR_BENCH_WATCHDOG_S", "900")))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

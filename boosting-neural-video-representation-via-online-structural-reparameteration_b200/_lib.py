@@ -122,9 +122,20 @@ def last_error():
     return load().onr_last_error().decode(errors="replace")
 
 
+_SYNC_DEBUG = bool(os.environ.get("ONR_SYNC_DEBUG"))
+
+
 def check(rc, what=""):
     if rc != 0:
         raise RuntimeError(f"liborepnerv {what} failed (rc={rc}): {last_error()}")
+    if _SYNC_DEBUG:
+        # debugging aid: serialise after every library call and leave a trail (the last line printed before a hang
+        # names the kernel that never finished)
+        import sys
+        import torch
+        print(f"[onr] {what} ...", file=sys.stderr, end="", flush=True)
+        torch.cuda.synchronize()
+        print(" ok", file=sys.stderr, flush=True)
 
 
 def lib():

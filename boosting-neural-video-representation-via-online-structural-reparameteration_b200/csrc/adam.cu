@@ -9,6 +9,8 @@
 
 namespace onr {
 
+constexpr size_t kAdamPerBlock = 256 * 4 * 4;      // elements per block per sweep (4 float4 per thread)
+
 struct AdamEntry {
     uint64_t p, g, m, v, n;
 };
@@ -19,6 +21,9 @@ adam_multi_kernel(const AdamEntry* __restrict__ table, const float* __restrict__
                   int zero_grad) {
     const AdamEntry e = table[blockIdx.y];
     const size_t n = (size_t)e.n;
+    // blocks beyond this tensor's share exit immediately; small tensors use one block
+    const size_t my_blocks = (n + kAdamPerBlock - 1) / kAdamPerBlock;
+    if (blockIdx.x >= my_blocks) return;
     const size_t start = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (start >= n) return;
     float* __restrict__ p = reinterpret_cast<float*>(e.p);
@@ -30,7 +35,7 @@ adam_multi_kernel(const AdamEntry* __restrict__ table, const float* __restrict__
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)t));
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)t));
     const float step_size = lr / bc1;
-    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    const size_t stride = (size_t)(my_blocks < gridDim.x ? my_blocks : gridDim.x) * blockDim.x * 4;
     const bool vec_ok = ((e.p | e.g | e.m | e.v) & 15ull) == 0;
     for (size_t i = start; i < n; i += stride) {
         if (vec_ok && i + 4 <= n) {
@@ -101,9 +106,9 @@ extern "C" int onr_adam_multi(const uint64_t* table, int n_tensors, size_t max_n
                               int zero_grad, void* stream) {
     using namespace onr;
     ONR_REQUIRE(n_tensors >= 1 && n_tensors <= 65535, "adam: bad tensor count %d", n_tensors);
-    size_t bx = (max_numel + 256 * 4 * 4 - 1) / (256 * 4 * 4);   // ~4 float4 per thread on the largest tensor
+    size_t bx = (max_numel + kAdamPerBlock - 1) / kAdamPerBlock;   // ~4 float4 per thread on the largest tensor
     if (bx < 1) bx = 1;
-    if (bx > 1024) bx = 1024;
+    if (bx > 296) bx = 296;                                        // two blocks per SM on the big tensors
     dim3 grid((unsigned)bx, (unsigned)n_tensors);
     adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const AdamEntry*>(table), lr_dev,
                                                              step_dev, beta1, beta2, eps, grad_scale, zero_grad);

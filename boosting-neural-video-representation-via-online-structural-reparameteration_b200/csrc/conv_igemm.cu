@@ -71,7 +71,7 @@ __device__ __forceinline__ long long clk() { return clock64(); }
 struct __align__(8) SmemBarriers {
     uint64_t a_full[kMaxRing], a_empty[kMaxRing];
     uint64_t b_full[kMaxRing], b_empty[kMaxRing];
-    uint64_t tmem_full[2], tmem_empty[2], tile_started[2];
+    uint64_t tmem_full[2], tmem_empty[2], turn[2];
     uint32_t tmem_base;
 };
 
@@ -137,7 +137,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bars->tmem_full[b]), p.issuers);
-            mbar_init(smem_u32(&bars->tile_started[b]), 1);
+            mbar_init(smem_u32(&bars->turn[b]), 1);
             mbar_init(smem_u32(&bars->tmem_empty[b]), kEpiThreads);
         }
         fence_mbar_init();
@@ -219,13 +219,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         // ===================================================================== UMMA issuers
         // A K-group = one A box (chunk, dw) and its three vertical taps: 3 * (width/16) * MS MMAs, then one burst
         // of commits (3 weight slots + the A slot).  csrc/mma_bench.cu: a commit drains the issuing thread's MMAs
-        // (~600 cycles) before it can issue again, but two issuer warps overlap each other's drains
-        // (N=192: 1949 -> 3848 MAC/clk/SM).  So kIssuers warps take alternate K-groups of the SAME tile; the
-        // tensor pipe executes MMAs in arrival order, and the issuer of a tile's first (overwriting) group
-        // releases the others through `tile_started`.
+        // (~600 cycles) before that thread can issue again, but a second issuer warp overlaps the drain
+        // (N=192: 1949 -> 3848 MAC/clk/SM).  So the issuer warps take alternate K-groups of the SAME tile.
+        //
+        // Ordering protocol (alias-free by construction): groups are ISSUED in strict global order.  The owner of
+        // group g waits for `turn[me]` (arrived by the other issuer right after it issued group g-1, before its
+        // commits), then waits for its own group's full barriers, issues, passes the turn, and only then commits
+        // (= drains).  Because every earlier group was issued after its data had landed, every earlier phase of
+        // every ring slot is complete when an owner waits, so a parity wait can never see a stale phase — even if
+        // an issuer warp is starved for a long time by co-resident kernels.  Nobody waits on a barrier phase it
+        // does not consume.  The tile's first (overwriting) group is trivially issued first.
         const int me = warp - kWarpMma0;
         const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
-        uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, gidx = 0;
+        uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, gidx = 0, turn_waits = 0;
         int it = 0;
         const bool prof = p.prof != nullptr && me == 0;
         long long t_start = prof ? clk() : 0, w_a = 0, w_b = 0, w_t = 0, t0 = 0;
@@ -237,7 +243,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
             if (prof) w_t += clk() - t0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * p.ms * p.block_n;
-            bool first_group = true, joined = false;
+            bool first_group = true;
             for (int ch = 0; ch < p.chunks; ++ch) {
                 const Chunk c = chunk_of(p, ch);
                 const uint32_t row_b = c.width == 64 ? 1024u : 512u;   // bytes per image row of the box == SBO
@@ -245,26 +251,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                 const int ksl = c.width / 16;
                 for (int dwi = 0; dwi < 3; ++dwi, ++gidx, first_group = false) {
                     const bool mine = (gidx % (uint32_t)p.issuers) == (uint32_t)me;
-                    uint32_t b_s[3], b_bar[3];
-                    if (mine && !first_group && !joined) {
-                        mbar_wait(smem_u32(&bars->tile_started[buf]), acc_phase);
-                        joined = true;
-                    }
-                    // EVERY issuer observes EVERY phase of the full barriers, in order, even for groups it does
-                    // not own: a parity wait cannot tell phase k from phase k+2, so an issuer that skipped the other
-                    // issuer's groups could sail through a stale phase (guaranteed with a 3-slot ring).
-                    if (prof) t0 = clk();
-                    mbar_wait(smem_u32(&bars->a_full[aslot]), aphase);
-                    if (prof) { const long long t1 = clk(); w_a += t1 - t0; t0 = t1; }
+                    uint32_t b_s[3], b_bar[3], b_full[3], b_par[3];
                     uint32_t bs = bslot, bp = bphase;
 #pragma unroll
                     for (int dhi = 0; dhi < 3; ++dhi) {
-                        mbar_wait(smem_u32(&bars->b_full[bs]), bp);
                         b_s[dhi] = b_ring + bs * p.b_bytes;
                         b_bar[dhi] = smem_u32(&bars->b_empty[bs]);
+                        b_full[dhi] = smem_u32(&bars->b_full[bs]);
+                        b_par[dhi] = bp;
                         if (++bs == (uint32_t)p.nb) { bs = 0; bp ^= 1; }
                     }
                     if (mine) {
+                        if (p.issuers > 1 && gidx > 0) {
+                            mbar_wait(smem_u32(&bars->turn[me]), turn_waits & 1u);   // group gidx-1 has been issued
+                            ++turn_waits;
+                        }
+                        if (prof) t0 = clk();
+                        mbar_wait(smem_u32(&bars->a_full[aslot]), aphase);
+                        if (prof) { const long long t1 = clk(); w_a += t1 - t0; t0 = t1; }
+#pragma unroll
+                        for (int dhi = 0; dhi < 3; ++dhi) mbar_wait(b_full[dhi], b_par[dhi]);
                         if (prof) w_b += clk() - t0;
                         tc_fence_after();
                         const uint32_t a_s = a_ring + aslot * p.a_bytes;
@@ -282,13 +288,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                                     }
                                 }
                             }
-                            if (first_group) mbar_arrive(smem_u32(&bars->tile_started[buf]));
+                            if (p.issuers > 1) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));   // pass the turn, then drain
 #pragma unroll
                             for (int dhi = 0; dhi < 3; ++dhi) umma_commit(b_bar[dhi]);
                             umma_commit(smem_u32(&bars->a_empty[aslot]));
                         }
                         __syncwarp();
-                        if (first_group) joined = true;
                     }
                     bslot = bs;
                     bphase = bp;

@@ -33,6 +33,7 @@ struct GemmArgs {
     int accumulate;  // C += A*B when non-zero
     int k_chunk;     // split-K: blockIdx.z handles k in [z*k_chunk, (z+1)*k_chunk); partials are combined
                      // with atomicAdd (only legal with accumulate != 0, i.e. C already holds its addend)
+    int contiguous_c;  // C is a plain row-major [M][N] array (used to zero it before a split-K overwrite)
 };
 
 constexpr int GT = 64, GK = 16;
@@ -100,6 +101,11 @@ __global__ void __launch_bounds__(256) strided_gemm_kernel(const GemmArgs g) {
 static int launch_gemm(GemmArgs g, cudaStream_t st, bool allow_split = false) {
     const int tiles = ceil_div(g.N, GT) * ceil_div(g.M, GT);
     int splits = 1;
+    if (!g.accumulate && allow_split && g.contiguous_c && tiles < num_sms()) {
+        // overwrite semantics with split-K: zero C, then accumulate partials atomically
+        ONR_CUDA(cudaMemsetAsync(g.C, 0, (size_t)g.M * g.N * sizeof(float), st));
+        g.accumulate = 1;
+    }
     if (g.accumulate && allow_split) {
         // enough CTAs to cover the machine twice, but at least 64 k-elements of work per CTA
         splits = ceil_div(2 * num_sms(), tiles);
@@ -247,13 +253,13 @@ int onr_erb_fold_fwd(const float* w3x3, const float* b3x3, const float* w1x3, co
     // T[(o,hw), i] = sum_m W2[o,m,hw] * W1[m,i]
     GemmArgs g1{w2, w1, T, Cout * 9, Cin, C2,
                 ax2(9, (long long)C2 * 9, 1), ax(9), ax(Cin), ax(1),
-                ax2(9, (long long)Cin * 9, 1), ax(9), 0, 0};
+                ax2(9, (long long)Cin * 9, 1), ax(9), 0, 0, 0};
     int rc = launch_gemm(g1, st);
     if (rc) return rc;
     // K[p, (i,hw)] += sum_o W3[p,o] * T[o,(i,hw)]
     GemmArgs g2{w3, T, K, Cout, Cin * 9, Cout,
                 ax(Cout), ax(1), ax((long long)Cin * 9), ax(1),
-                ax((long long)Cin * 9), ax(1), 1, 0};
+                ax((long long)Cin * 9), ax(1), 1, 0, 0};
     return launch_gemm(g2, st);
 }
 
@@ -269,23 +275,23 @@ int onr_erb_fold_bwd(const float* dK, const float* dbias, const float* w1, const
                                                                            g1x3, gb1x3, g3x1, gb3x1);
     ONR_LAUNCH_CHECK();
     // gW3[p,o] += sum_x dK[p,x] T[o,x]
-    GemmArgs a{dK, T, gw3, Cout, Cout, (int)CK, ax(CK), ax(1), ax(1), ax(CK), ax(Cout), ax(1), 1, 0};
+    GemmArgs a{dK, T, gw3, Cout, Cout, (int)CK, ax(CK), ax(1), ax(1), ax(CK), ax(Cout), ax(1), 1, 0, 0};
     int rc = launch_gemm(a, st, true);
     if (rc) return rc;
     // dT[o,x] = sum_p W3[p,o] dK[p,x]
-    GemmArgs b{w3, dK, dT, Cout, (int)CK, Cout, ax(1), ax(Cout), ax(CK), ax(1), ax(CK), ax(1), 0, 0};
-    rc = launch_gemm(b, st);
+    GemmArgs b{w3, dK, dT, Cout, (int)CK, Cout, ax(1), ax(Cout), ax(CK), ax(1), ax(CK), ax(1), 0, 0, 1};
+    rc = launch_gemm(b, st, true);
     if (rc) return rc;
     // gW2[(o,hw), m] += sum_i dT[o,i,hw] W1[m,i]
     GemmArgs c{dT, w1, gw2, Cout * 9, C2, Cin,
                ax2(9, CK, 1), ax(9), ax(1), ax(Cin),
-               ax2(9, (long long)C2 * 9, 1), ax(9), 1, 0};
+               ax2(9, (long long)C2 * 9, 1), ax(9), 1, 0, 0};
     rc = launch_gemm(c, st, true);
     if (rc) return rc;
     // gW1[m,i] += sum_{(o,hw)} W2[o,m,hw] dT[o,i,hw]
     GemmArgs d{w2, dT, gw1, C2, Cin, Cout * 9,
                ax(9), ax2(9, (long long)C2 * 9, 1), ax2(9, CK, 1), ax(9),
-               ax(Cin), ax(1), 1, 0};
+               ax(Cin), ax(1), 1, 0, 0};
     return launch_gemm(d, st, true);
 }
 

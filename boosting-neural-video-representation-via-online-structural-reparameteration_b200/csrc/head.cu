@@ -75,40 +75,56 @@ __global__ void head_bwd_kernel(const float* __restrict__ gimg, const float* __r
 #pragma unroll
         for (int e = 0; e < 8; ++e) gw[k][e] = 0.0f;
     if (lane < lanes) {
-        for (size_t pix = (size_t)blockIdx.x * lanes + lane; pix < npix; pix += (size_t)gridDim.x * lanes) {
-            const size_t b = pix / HW, hw = pix % HW;
-            const size_t io = b * 3 * (size_t)HW + hw;
-            float gp[3];
+        // two pixels per iteration: all global loads of both pixels are issued before any use (memory-level
+        // parallelism; the kernel is pure HBM streaming: y + SiLU' in, dz out)
+        const size_t stride = (size_t)gridDim.x * lanes;
+        for (size_t pix0 = (size_t)blockIdx.x * lanes + lane; pix0 < npix; pix0 += 2 * stride) {
+            const size_t pixs[2] = {pix0, pix0 + stride};
+            uint4 yv[2], dv[2];
+            float gp[2][3];
+            bool ok[2];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float o = img[io + k * (size_t)HW];
-                const float g = gimg[io + k * (size_t)HW];
-                gp[k] = use_sigmoid ? g * o * (1.0f - o) : g * 2.0f * o * (1.0f - o);
-            }
-            const uint4 yv = __ldg(reinterpret_cast<const uint4*>(y + pix * Cp) + ch);
-            const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dsilu + pix * Cp) + ch);
-            const uint32_t yu[4] = {yv.x, yv.y, yv.z, yv.w};
-            const uint32_t du[4] = {dv.x, dv.y, dv.z, dv.w};
-            uint32_t out[4];
+            for (int u = 0; u < 2; ++u) {
+                ok[u] = pixs[u] < npix;
+                if (ok[u]) {
+                    yv[u] = __ldg(reinterpret_cast<const uint4*>(y + pixs[u] * Cp) + ch);
+                    dv[u] = __ldg(reinterpret_cast<const uint4*>(dsilu + pixs[u] * Cp) + ch);
+                    const size_t b = pixs[u] / HW, hw = pixs[u] % HW;
+                    const size_t io = b * 3 * (size_t)HW + hw;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = ch * 8 + e * 2;
-                const float y0 = bf16_lo(yu[e]), y1 = bf16_hi(yu[e]);
-                float d0 = 0.0f, d1 = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    gw[k][e * 2] = fmaf(gp[k], y0, gw[k][e * 2]);
-                    gw[k][e * 2 + 1] = fmaf(gp[k], y1, gw[k][e * 2 + 1]);
-                    d0 = fmaf(gp[k], sw[k * Cp + c], d0);
-                    d1 = fmaf(gp[k], sw[k * Cp + c + 1], d1);
+                    for (int k = 0; k < 3; ++k) {
+                        const float o = __ldg(img + io + k * (size_t)HW);
+                        const float g = __ldg(gimg + io + k * (size_t)HW);
+                        gp[u][k] = use_sigmoid ? g * o * (1.0f - o) : g * 2.0f * o * (1.0f - o);
+                    }
                 }
-                out[e] = pack_bf16x2(d0 * bf16_lo(du[e]), d1 * bf16_hi(du[e]));
             }
-            reinterpret_cast<uint4*>(dz + pix * Cp)[ch] = make_uint4(out[0], out[1], out[2], out[3]);
-            if (ch == 0) {
-                gb[0] += gp[0];
-                gb[1] += gp[1];
-                gb[2] += gp[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!ok[u]) continue;
+                const uint32_t yu[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+                const uint32_t du[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+                uint32_t out[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = ch * 8 + e * 2;
+                    const float y0 = bf16_lo(yu[e]), y1 = bf16_hi(yu[e]);
+                    float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        gw[k][e * 2] = fmaf(gp[u][k], y0, gw[k][e * 2]);
+                        gw[k][e * 2 + 1] = fmaf(gp[u][k], y1, gw[k][e * 2 + 1]);
+                        d0 = fmaf(gp[u][k], sw[k * Cp + c], d0);
+                        d1 = fmaf(gp[u][k], sw[k * Cp + c + 1], d1);
+                    }
+                    out[e] = pack_bf16x2(d0 * bf16_lo(du[e]), d1 * bf16_hi(du[e]));
+                }
+                reinterpret_cast<uint4*>(dz + pixs[u] * Cp)[ch] = make_uint4(out[0], out[1], out[2], out[3]);
+                if (ch == 0) {
+                    gb[0] += gp[u][0];
+                    gb[1] += gp[u][1];
+                    gb[2] += gp[u][2];
+                }
             }
         }
 #pragma unroll
@@ -153,7 +169,7 @@ int onr_head_bwd(const float* gimg, const float* img, const void* y, const void*
     const int lanes = 384 / chunks;
     const int threads = lanes * chunks;
     int grid = (int)((npix + lanes - 1) / lanes);
-    if (grid > num_sms() * 4) grid = num_sms() * 4;
+    if (grid > num_sms() * 5) grid = num_sms() * 5;
     head_bwd_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
         gimg, img, reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dsilu),
         npix, H * W, C, Cp, Wh, use_sigmoid, gWh, gbh, reinterpret_cast<__nv_bfloat16*>(dz));

@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) device; run with `-m gpu`")
+    # a wedged GPU wait must fail the test instead of hanging the run (pytest-timeout is in the image)
+    if config.pluginmanager.hasplugin("timeout") and not config.getoption("timeout", None):
+        config.option.timeout = 900
 
 
 @pytest.fixture(scope="session")
