@@ -50,7 +50,7 @@ class ClockSampler:
     (An external `nvidia-smi -lms 100` poller next to the persistent tcgen05 kernels coincided with GPU-side hangs
     on this driver — see DESIGN.md section 6 — so nothing is spawned here.)"""
 
-    def __init__(self, gpu_index, period_s=0.25):
+    def __init__(self, gpu_index, period_s=0.02):
         self.gpu, self.period, self.rows, self.thread = gpu_index, period_s, [], None
         self._stop = threading.Event()
         self.mode = os.environ.get("ONR_BENCH_SAMPLER", "nvml")      # nvml | smi | off

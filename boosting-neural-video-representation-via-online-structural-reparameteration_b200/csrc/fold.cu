@@ -36,57 +36,79 @@ struct GemmArgs {
     int contiguous_c;  // C is a plain row-major [M][N] array (used to zero it before a split-K overwrite)
 };
 
-constexpr int GT = 64, GK = 16;
+constexpr int GK = 16;
 
+// TM x TN output tile per 256-thread block, GK-deep K slabs.  The next slab is fetched into registers while the
+// current one is multiplied (the contractions are small and latency-bound: K <= 5850, a few hundred CTAs at most).
+template <int TM, int TN>
 __global__ void __launch_bounds__(256) strided_gemm_kernel(const GemmArgs g) {
-    __shared__ float As[GK][GT + 1];
-    __shared__ float Bs[GK][GT + 1];
-    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    constexpr int RM = TM / 16, RN = TN / 16;              // per-thread register block
+    constexpr int LA = TM * GK / 256, LB = TN * GK / 256;  // elements each thread stages per slab
+    __shared__ float As[GK][TM + 1];
+    __shared__ float Bs[GK][TN + 1];
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-    float acc[4][4] = {};
+    float acc[RM][RN] = {};
     const int k_begin = blockIdx.z * g.k_chunk;
     const int k_end = min(g.K, k_begin + g.k_chunk);
     const bool split = gridDim.z > 1;
-    // loader mapping: 256 threads load 64x16 A and 16x64 B: 4 elements each
+    // loop-invariant parts of the staging addresses
+    long long a_off[LA], b_off[LB];
+    int a_m[LA], a_k[LA], b_k[LB], b_n[LB];
+#pragma unroll
+    for (int l = 0; l < LA; ++l) {
+        const int e = threadIdx.x + l * 256;
+        a_m[l] = e / GK; a_k[l] = e % GK;
+        a_off[l] = (m0 + a_m[l] < g.M) ? axis_off(g.am, m0 + a_m[l]) : -1;
+    }
+#pragma unroll
+    for (int l = 0; l < LB; ++l) {
+        const int e = threadIdx.x + l * 256;
+        b_k[l] = e / TN; b_n[l] = e % TN;
+        b_off[l] = (n0 + b_n[l] < g.N) ? axis_off(g.bn, n0 + b_n[l]) : -1;
+    }
+    float ra[LA], rb[LB];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int l = 0; l < LA; ++l) {
+            const int k = k0 + a_k[l];
+            ra[l] = (a_off[l] >= 0 && k < k_end) ? g.A[a_off[l] + axis_off(g.ak, k)] : 0.0f;
+        }
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            const int k = k0 + b_k[l];
+            rb[l] = (b_off[l] >= 0 && k < k_end) ? g.B[axis_off(g.bk, k) + b_off[l]] : 0.0f;
+        }
+    };
+    fetch(k_begin);
     for (int k0 = k_begin; k0 < k_end; k0 += GK) {
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            const int e = threadIdx.x + l * 256;
-            {   // A tile: e -> (m = e / 16, k = e % 16)
-                const int m = e / GK, k = e % GK;
-                float v = 0.0f;
-                if (m0 + m < g.M && k0 + k < k_end) v = g.A[axis_off(g.am, m0 + m) + axis_off(g.ak, k0 + k)];
-                As[k][m] = v;
-            }
-            {   // B tile: e -> (k = e / 64, n = e % 64)
-                const int k = e / GT, n = e % GT;
-                float v = 0.0f;
-                if (n0 + n < g.N && k0 + k < k_end) v = g.B[axis_off(g.bk, k0 + k) + axis_off(g.bn, n0 + n)];
-                Bs[k][n] = v;
-            }
-        }
+        for (int l = 0; l < LA; ++l) As[a_k[l]][a_m[l]] = ra[l];
+#pragma unroll
+        for (int l = 0; l < LB; ++l) Bs[b_k[l]][b_n[l]] = rb[l];
         __syncthreads();
+        if (k0 + GK < k_end) fetch(k0 + GK);
 #pragma unroll
         for (int k = 0; k < GK; ++k) {
-            float a[4], b[4];
+            float a[RM], b[RN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+            for (int i = 0; i < RM; ++i) a[i] = As[k][ty * RM + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+            for (int j = 0; j < RN; ++j) b[j] = Bs[k][tx * RN + j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < RM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < RM; ++i) {
+        const int m = m0 + ty * RM + i;
         if (m >= g.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
+        for (int j = 0; j < RN; ++j) {
+            const int n = n0 + tx * RN + j;
             if (n >= g.N) continue;
             float* c = g.C + axis_off(g.cm, m) + axis_off(g.cn, n);
             if (split) atomicAdd(c, acc[i][j]);
@@ -99,7 +121,10 @@ __global__ void __launch_bounds__(256) strided_gemm_kernel(const GemmArgs g) {
 // from run to run).  Used for gradients only; the forward fold stays deterministic so that a deploy
 // checkpoint reproduces the train-state decode bit for bit (reference main_train.py:332-349).
 static int launch_gemm(GemmArgs g, cudaStream_t st, bool allow_split = false) {
-    const int tiles = ceil_div(g.N, GT) * ceil_div(g.M, GT);
+    // 64x64 tiles when they already cover the machine, 32x32 tiles (4x the CTAs) otherwise
+    const int tiles64 = ceil_div(g.N, 64) * ceil_div(g.M, 64);
+    const int T = tiles64 >= num_sms() ? 64 : 32;
+    const int tiles = ceil_div(g.N, T) * ceil_div(g.M, T);
     int splits = 1;
     if (!g.accumulate && allow_split && g.contiguous_c && tiles < num_sms()) {
         // overwrite semantics with split-K: zero C, then accumulate partials atomically
@@ -115,8 +140,9 @@ static int launch_gemm(GemmArgs g, cudaStream_t st, bool allow_split = false) {
     }
     g.k_chunk = ceil_div(ceil_div(g.K, splits), GK) * GK;
     splits = ceil_div(g.K, g.k_chunk);
-    dim3 grid(ceil_div(g.N, GT), ceil_div(g.M, GT), splits);
-    strided_gemm_kernel<<<grid, 256, 0, st>>>(g);
+    dim3 grid(ceil_div(g.N, T), ceil_div(g.M, T), splits);
+    if (T == 64) strided_gemm_kernel<64, 64><<<grid, 256, 0, st>>>(g);
+    else strided_gemm_kernel<32, 32><<<grid, 256, 0, st>>>(g);
     ONR_LAUNCH_CHECK();
     return 0;
 }
