@@ -222,13 +222,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         // (~600 cycles) before that thread can issue again, but a second issuer warp overlaps the drain
         // (N=192: 1949 -> 3848 MAC/clk/SM).  So the issuer warps take alternate K-groups of the SAME tile.
         //
-        // Ordering protocol (alias-free by construction): groups are ISSUED in strict global order.  The owner of
-        // group g waits for `turn[me]` (arrived by the other issuer right after it issued group g-1, before its
-        // commits), then waits for its own group's full barriers, issues, passes the turn, and only then commits
-        // (= drains).  Because every earlier group was issued after its data had landed, every earlier phase of
-        // every ring slot is complete when an owner waits, so a parity wait can never see a stale phase — even if
-        // an issuer warp is starved for a long time by co-resident kernels.  Nobody waits on a barrier phase it
-        // does not consume.  The tile's first (overwriting) group is trivially issued first.
+        // Ordering protocol (alias-free by construction): groups WAIT FOR THEIR DATA in strict global order.  The
+        // owner of group g waits for `turn[me]` (arrived by the owner of group g-1 once ITS data had landed), then
+        // for its own group's full barriers, passes the turn, issues and commits (= drains).  By induction every
+        // earlier phase of every ring slot is complete when an owner waits, so a parity wait can never see a stale
+        // phase — even if an issuer warp is starved for microseconds by co-resident side-stream kernels (this was
+        // an intermittent deadlock with a looser scheme).  Nobody waits on a barrier phase it does not consume.
         const int me = warp - kWarpMma0;
         const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
         uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, gidx = 0, turn_waits = 0;
@@ -275,6 +274,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                         tc_fence_after();
                         const uint32_t a_s = a_ring + aslot * p.a_bytes;
                         if (elect_one()) {
+                            // The turn only has to guarantee that every earlier group has finished WAITING for its
+                            // data, so it is passed on before issuing (both issuers then issue concurrently; issue
+                            // rate, not the tensor pipe, limits N = 96 MMAs).  Exception: a tile's first group
+                            // overwrites the accumulator and must reach the tensor pipe first.
+                            if (p.issuers > 1 && !first_group) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));
 #pragma unroll
                             for (int dhi = 0; dhi < 3; ++dhi) {
                                 for (int k = 0; k < ksl; ++k) {
@@ -288,7 +292,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                                     }
                                 }
                             }
-                            if (p.issuers > 1) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));   // pass the turn, then drain
+                            if (p.issuers > 1 && first_group) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));
 #pragma unroll
                             for (int dhi = 0; dhi < 3; ++dhi) umma_commit(b_bar[dhi]);
                             umma_commit(smem_u32(&bars->a_empty[aslot]));
