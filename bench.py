@@ -303,8 +303,14 @@ def run_ours(opts):
         kern[name] = a.elapsed_time(b) / 10.0
     dom = max(kern, key=kern.get)
     achieved = L4_GEMM_GFLOP / kern[dom]            # GFLOP / ms = TFLOP/s
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks['bf16'], "unit": "TFLOP/s",
-                "frac": achieved / peaks['bf16'], "traffic": None, "peak_source": peaks['source'] + " bf16 burst",
+                "frac": achieved / peaks['bf16'], "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                "peak_source": peaks['source'] + " bf16 burst",
                 "algorithmic_gflop_per_launch": L4_GEMM_GFLOP,
                 "launch_ms": {k: round(v, 4) for k, v in kern.items()},
                 "step_tflops": STEP_GFLOP / (ms / opts.steps), "step_frac_of_sustained": STEP_GFLOP / (ms / opts.steps) / peaks['bf16_sustained']}
