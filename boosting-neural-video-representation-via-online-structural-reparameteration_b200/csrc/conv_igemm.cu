@@ -117,13 +117,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                   const __grid_constant__ CUtensorMap tmD64, const __grid_constant__ CUtensorMap tmD32,
                   const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [na x A slot] [nb x B slot] [staging 2 x 2 x 8 KB] [barriers]
+    // carve: [na x A slot] [nb x B slot] [staging: y 16 KB | d 16 KB] [barriers]
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_ring = smem_base;
     const uint32_t b_ring = a_ring + p.na * p.a_bytes;
     const uint32_t staging = b_ring + p.nb * p.b_bytes;
     SmemBarriers* bars =
-        reinterpret_cast<SmemBarriers*>(smem_raw + (staging + 4 * kStageOutBytes - smem_u32(smem_raw)));
+        reinterpret_cast<SmemBarriers*>(smem_raw + (staging + 2 * kStageOutBytes - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -278,7 +278,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                             // data, so it is passed on before issuing (both issuers then issue concurrently; issue
                             // rate, not the tensor pipe, limits N = 96 MMAs).  Exception: a tile's first group
                             // overwrites the accumulator and must reach the tensor pipe first.
-                            if (p.issuers > 1 && !first_group) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));
+                            // Decode plans (FPROP_INFER) keep strict issue order instead: the accumulation order, hence
+                            // every output bit, is then reproducible run to run (a decoder must be deterministic).
+                            const bool early = !first_group && p.mode != ONR_CONV_FPROP_INFER;
+                            if (p.issuers > 1 && early) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));
 #pragma unroll
                             for (int dhi = 0; dhi < 3; ++dhi) {
                                 for (int k = 0; k < ksl; ++k) {
@@ -292,7 +295,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                                     }
                                 }
                             }
-                            if (p.issuers > 1 && first_group) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));
+                            if (p.issuers > 1 && !early) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));
 #pragma unroll
                             for (int dhi = 0; dhi < 3; ++dhi) umma_commit(b_bar[dhi]);
                             umma_commit(smem_u32(&bars->a_empty[aslot]));
@@ -349,10 +352,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                     const int ojc = n_g - oi * p.out_jc;
                     const bool wide = (g * 64 + 64 <= p.block_n) && (n_g + 64 <= p.n_total) && (ojc % 64 == 0) &&
                                       (ojc + 64 <= p.out_jc);
-                    const uint32_t sbuf = iter_ctr & 1u;
+                    const uint32_t sbuf = 0;   // single staging buffer: the weight ring needs the shared memory more
                     ++iter_ctr;
                     if (prof) t0 = clk();
-                    if (store_thread) tma_store_wait_read<1>();
+                    if (store_thread) tma_store_wait_read<0>();
                     if (prof) e_store += clk() - t0;
                     named_bar_sync(1, kEpiThreads);
                     const uint32_t ybuf = staging + sbuf * 2 * kStageOutBytes;
@@ -569,7 +572,7 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     p.a_bytes = (p.a_bytes + 1023) / 1024 * 1024;       // keep every slot 1024-aligned
     p.b_bytes = block_n * wmax * 2;                     // multiple of 2048
     // ring depths: ~96 KB of A boxes at most, the rest for weight tiles
-    const int budget = kMaxDynSmem - 1024 - 4 * kStageOutBytes - (int)sizeof(SmemBarriers) - 1024;
+    const int budget = kMaxDynSmem - 1024 - 2 * kStageOutBytes - (int)sizeof(SmemBarriers) - 1024;
     // one A box feeds three weight tiles, so two or three A slots are enough; weight tiles get the rest
     int na = 3;
     while (na > 2 && (na * p.a_bytes > budget / 2 || (budget - na * p.a_bytes) / p.b_bytes < 6)) --na;
@@ -580,7 +583,7 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     while (na < 4 && (na + 1) * p.a_bytes + nb * p.b_bytes <= budget) ++na;
     p.na = na;
     p.nb = nb;
-    pl->smem = 1024 + (size_t)na * p.a_bytes + (size_t)nb * p.b_bytes + 4 * kStageOutBytes + sizeof(SmemBarriers);
+    pl->smem = 1024 + (size_t)na * p.a_bytes + (size_t)nb * p.b_bytes + 2 * kStageOutBytes + sizeof(SmemBarriers);
     pl->grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     // 64-channel maps only exist when the channel extent allows them; otherwise they alias the 32-wide ones
     const int a64 = p.cj >= 64 ? 64 : 32, o64 = p.out_jc >= 64 ? 64 : 32, b64 = k_tap >= 64 ? 64 : 32;

@@ -408,3 +408,36 @@ def test_cli_train_then_eval(dev, tmp_path, monkeypatch):
     psnr_pq, _ = main_eval.main(flags + ['--eval_only', '--prune_ratio', '0.2', '--quant_bit', '8'])
     assert psnr_full > 5.0 and psnr_pq > 5.0 and abs(psnr_full - psnr_pq) < 3.0
     assert (out / 'only_prune0.20_quant8.txt').exists() and (out / 'bpp_rank0.txt').exists()
+
+
+@pytest.mark.parametrize("cfg,bt", [
+    (dict(embed='1.25_40', stem_dim_num='64_1', fc_hw_dim='2_3_112', expansion=1, reduction=2, lower_width=96,
+          strides=[5, 2]), "ERB"),                      # NeRV-L width (BASELINE configs[2]): 112 -> 2800 -> 112 -> 384
+    (dict(embed='1.25_40', stem_dim_num='64_1', fc_hw_dim='2_3_26', expansion=1, reduction=2, lower_width=96,
+          strides=[5, 3, 2]), "ERB"),                   # UVG stride list 5 3 2 (BASELINE configs[3]): N = 864 block
+    (dict(embed='1.25_40', stem_dim_num='64_1', fc_hw_dim='2_3_26', expansion=1, reduction=2, lower_width=96,
+          strides=[5, 3, 2]), "NeRV_vanilla"),
+])
+def test_generator_other_geometries_vs_oracle(dev, cfg, bt):
+    """Channel widths / strides of the other BASELINE configs at a small spatial size: image, loss and every
+    parameter gradient against the CPU oracle (fp32), same seed and target."""
+    from orepnerv.utils import loss_fn
+    pe, gen = build(cfg, bt, dev)
+    sd = {k: v.detach().cpu().clone() for k, v in gen.state_dict().items()}
+    pos = torch.tensor([0.125, 0.625])
+    img = gen(pe(pos))[0]
+    H, W = img.shape[-2:]
+    g = torch.Generator().manual_seed(21)
+    target = torch.randint(0, 256, (2, 3, H, W), generator=g).float().div(255)
+    loss = loss_fn(img, target.to(dev), argparse.Namespace(loss_type='Fusion6'))
+    loss.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    img_ref = O.generator_forward(params, O.pos_encoding(pos, 1.25, 40), ocfg(cfg))
+    loss_ref = O.loss_fn(img_ref, target)
+    grads_ref = torch.autograd.grad(loss_ref, list(params.values()))
+    assert rel_l2(img, img_ref) <= 1e-2
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3
+    for (k, _), gr in zip(params.items(), grads_ref):
+        pg = dict(gen.named_parameters())[k].grad
+        err = (pg.cpu() - gr).norm().item()
+        assert err <= 4e-2 * gr.norm().item() + 1e-6, (k, err, gr.norm().item())
