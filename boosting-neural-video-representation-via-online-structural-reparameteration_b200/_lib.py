@@ -78,6 +78,8 @@ _SIGNATURES = {
     "onr_nhwc_bf16_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "onr_head_fwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
     "onr_head_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp]),
+    "onr_head_bwd_dz": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp]),
+    "onr_head_bwd_gw": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "onr_loss_workspace_bytes": (sz, [i32, i32, i32]),
     "onr_fusion6_fwd_bwd": (i32, [vp, vp, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp]),
     "onr_msssim_workspace_bytes": (sz, [i32, i32, i32]),

@@ -279,12 +279,25 @@ class NetExecutor:
         head = gen.head_conv()
         hname = gen.head_name()
         gL = self.geoms[-1]
-        check(lib.onr_head_bwd(
-            ptr(gimg), ptr(self.img), ptr(self.x[self.L]), ptr(self.d[self.L]), self.B, self.H, self.W,
-            self.C_last, gL.cpo, ptr(head.weight), 1 if gen.sigmoid else 0,
-            ptr(grads[hname + ".weight"]), ptr(grads[hname + ".bias"]), ptr(self.dz[self.L]), st), "onr_head_bwd")
         main = torch.cuda.current_stream()
         joins = []
+        # head backward: the weight/bias gradient reduction runs on a side stream (nothing downstream needs it
+        # before Adam); only dz = (Wh^T g_pre) * SiLU' stays on the critical path
+        fork = torch.cuda.Event()
+        fork.record(main)
+        hside = self._side_streams()[0]
+        hside.wait_event(fork)
+        with torch.cuda.stream(hside):
+            check(lib.onr_head_bwd_gw(
+                ptr(gimg), ptr(self.img), ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
+                1 if gen.sigmoid else 0, ptr(grads[hname + ".weight"]), ptr(grads[hname + ".bias"]), _lib.stream()),
+                "onr_head_bwd_gw")
+            ev = torch.cuda.Event()
+            ev.record(hside)
+            joins.append(ev)
+        check(lib.onr_head_bwd_dz(
+            ptr(gimg), ptr(self.img), ptr(self.d[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
+            ptr(head.weight), 1 if gen.sigmoid else 0, ptr(self.dz[self.L]), st), "onr_head_bwd_dz")
         for l in reversed(range(self.L)):
             g, blk = self.geoms[l], gen.layers[l]
             check(lib.onr_wgrad_plan_run(self.wgrad[l].handle, st), "onr_wgrad_plan_run")

@@ -165,6 +165,13 @@ int onr_head_bwd(const float* gimg, const float* img, const void* y_bf16, const 
                  int B, int H, int W, int C, int Cp, const float* Wh, int use_sigmoid,
                  float* gWh, float* gbh, void* dz_bf16, void* stream);
 
+/* The two halves of onr_head_bwd as separate launches (dz is on the critical path of the backward; the weight /
+ * bias gradient reduction is not and can run on another stream). */
+int onr_head_bwd_dz(const float* gimg, const float* img, const void* dsilu_bf16, int B, int H, int W, int C, int Cp,
+                    const float* Wh, int use_sigmoid, void* dz_bf16, void* stream);
+int onr_head_bwd_gw(const float* gimg, const float* img, const void* y_bf16, int B, int H, int W, int C, int Cp,
+                    int use_sigmoid, float* gWh, float* gbh, void* stream);
+
 /* ------------------------------------------------------------------ A7+A10: Fusion6 loss, PSNR, MS-SSIM
  * utils.py:159-160 with pytorch_msssim 0.2.1 ssim (11-tap sigma 1.5 valid windows, C1=1e-4, C2=9e-4),
  * utils.py:191-199 (psnr_fn).  pred/target NCHW fp32 [B][3][H][W].
