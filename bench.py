@@ -259,17 +259,29 @@ def run_ours(opts):
     pinned_frames = [clip[i:i + 1].cpu().pin_memory() for i in order[:8]]
     pinned_t = [(torch.tensor([i], dtype=torch.float32) / n_frames).pin_memory() for i in order[:8]]
     host_out = torch.zeros(8, dtype=torch.float32).pin_memory()
+    # public API for host-fed training: FrameFitter.host_pipeline_begin / step_host / host_pipeline_end.  Every step
+    # uploads its own pinned uint8 frame + index (H2D) and downloads its own metrics (D2H) inside the timed region;
+    # the copies run on a copy stream one step ahead / behind so they overlap the neighbouring steps' kernels.
+    fit.host_pipeline_begin(pinned_frames[0], pinned_t[0])
     for k in range(3):
-        fit.step(pinned_frames[k % 8], pinned_t[k % 8])
-        host_out.copy_(fit.out)
+        fit.step_host(pinned_frames[(k + 1) % 8], pinned_t[(k + 1) % 8])
+    fit.host_pipeline_end()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    results = []
     f0.record()
+    fit.host_pipeline_begin(pinned_frames[0], pinned_t[0])                   # H2D of step 0's inputs
     for k in range(opts.steps):
-        fit.step(pinned_frames[k % 8], pinned_t[k % 8])       # H2D frame + index, then the step
-        host_out.copy_(fit.out, non_blocking=False)           # D2H of [loss, L1, SSIM, MSE, PSNR, MS-SSIM, ..]
+        nxt = (k + 1) % 8
+        last = k == opts.steps - 1
+        prev = fit.step_host(None if last else pinned_frames[nxt], None if last else pinned_t[nxt])
+        if prev is not None:
+            results.append(prev)                                              # D2H result of step k-1, on the host
+    results.append(fit.host_pipeline_end())                                   # D2H result of the last step
     f1.record()
     barrier()
+    assert len(results) == opts.steps
+    host_out.copy_(results[-1])
     ms_e2e = f0.elapsed_time(f1)
     if world > 1:
         tms = torch.tensor([ms_e2e], device=dev)

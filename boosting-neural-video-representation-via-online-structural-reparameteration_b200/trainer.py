@@ -185,6 +185,70 @@ class FrameFitter:
         self.opt._step_count_host = self.host_step
         self.graph = g
 
+    # ------------------------------------------------------------------------------------------ host pipeline
+    # End-to-end driving from HOST buffers (what a data loader hands over): every step still uploads its own frame
+    # (uint8, pinned) + index and downloads its own metrics, but on a copy stream, one step ahead / behind, so the
+    # PCIe traffic overlaps the kernels of the neighbouring steps.
+    def host_pipeline_begin(self, frame_u8_host, t_host):
+        dev = self.dev
+        self._cs = torch.cuda.Stream(device=dev)
+        self._stage_f = [torch.empty_like(self.frame_u8) for _ in range(2)]
+        self._stage_t = [torch.empty_like(self.t_norm) for _ in range(2)]
+        self._ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        self._ev_used = [torch.cuda.Event() for _ in range(2)]
+        self._out_ring = torch.zeros(4, 8, dtype=torch.float32, device=dev)
+        self._host_ring = torch.zeros(4, 8, dtype=torch.float32).pin_memory()
+        self._ev_out = [torch.cuda.Event() for _ in range(4)]
+        self._ev_d2h = [torch.cuda.Event() for _ in range(4)]
+        self._hp_i = 0
+        self._hp_pending = None
+        self._prefetch(0, frame_u8_host, t_host, first=True)
+
+    def _prefetch(self, slot, frame_u8_host, t_host, first=False):
+        cs = self._cs
+        if not first:
+            cs.wait_event(self._ev_used[slot])          # the step that read this staging slot has consumed it
+        with torch.cuda.stream(cs):
+            self._stage_f[slot].copy_(frame_u8_host.reshape(self.frame_u8.shape), non_blocking=True)
+            self._stage_t[slot].copy_(t_host.reshape(self.t_norm.shape), non_blocking=True)
+            self._ev_h2d[slot].record(cs)
+
+    def step_host(self, next_frame_u8_host=None, next_t_host=None):
+        """Runs one step on the inputs prefetched earlier, prefetches the next step's inputs, and returns the
+        metrics of the PREVIOUS step as a host tensor (None on the first call)."""
+        i = self._hp_i
+        slot, r = i % 2, i % 4
+        main = torch.cuda.current_stream()
+        main.wait_event(self._ev_h2d[slot])
+        self.frame_u8.copy_(self._stage_f[slot], non_blocking=True)
+        self.t_norm.copy_(self._stage_t[slot], non_blocking=True)
+        self._ev_used[slot].record(main)
+        if next_frame_u8_host is not None:
+            self._prefetch((i + 1) % 2, next_frame_u8_host, next_t_host, first=(i == 0))
+        self.step()
+        self._out_ring[r].copy_(self.out, non_blocking=True)
+        self._ev_out[r].record(main)
+        self._cs.wait_event(self._ev_out[r])
+        with torch.cuda.stream(self._cs):
+            self._host_ring[r].copy_(self._out_ring[r], non_blocking=True)
+            self._ev_d2h[r].record(self._cs)
+        prev = None
+        if self._hp_pending is not None:
+            self._ev_d2h[self._hp_pending].synchronize()
+            prev = self._host_ring[self._hp_pending].clone()
+        self._hp_pending = r
+        self._hp_i = i + 1
+        return prev
+
+    def host_pipeline_end(self):
+        """Metrics of the last step (blocks until its download has landed)."""
+        if self._hp_pending is None:
+            return None
+        self._ev_d2h[self._hp_pending].synchronize()
+        out = self._host_ring[self._hp_pending].clone()
+        self._hp_pending = None
+        return out
+
     def sync_step_counter(self):
         """Align the device-side step counter with the host (call after loading a checkpoint)."""
         _, step_dev = self.opt.device_scalars(self.dev)
