@@ -9,19 +9,27 @@
 //   g3x3 += dK ; g1x3 += dK[:,:,1,:] ; g3x1 += dK[:,:,:,1] ; gb* += db
 //   gW3[p,o] += sum dK[p,.] T[o,.] ; dT = W3^T dK ; gW2[o,m,.] += sum_i dT[o,i,.] W1[m,i] ;
 //   gW1[m,i] += sum_{o,hw} W2[o,m,hw] dT[o,i,hw]
-// All contractions go through one strided fp32 GEMM kernel (64x64x16 tiles, 4x4 register blocks).
+// All contractions go through one strided fp32 GEMM kernel (32x32 tiles, four-way in-CTA split of each K slab).
 // Also: packing of an OIHW fp32 kernel into the bf16 implicit-GEMM operand layouts and back.
 #include "onr_common.cuh"
 
 namespace onr {
 
-// offset(idx) = (idx / div) * hi + (idx % div) * lo   — lets a GEMM index run over (channel, tap) pairs
+// offset(idx) = (idx / div) * hi + (idx % div) * lo   — lets a GEMM index run over (channel, tap) pairs.
+// A plain strided axis has div = 2^30 and takes the multiply-only path.
 struct Axis {
     int div;
     long long hi, lo;
 };
-__device__ __forceinline__ long long axis_off(const Axis& a, int idx) {
-    return (long long)(idx / a.div) * a.hi + (long long)(idx % a.div) * a.lo;
+__device__ __forceinline__ int axis_off(const Axis& a, int idx) {
+    if (idx < a.div) return idx * (int)a.lo;
+    return (idx / a.div) * (int)a.hi + (idx % a.div) * (int)a.lo;
+}
+static inline long long axis_extent(const Axis& a, int n) {   // largest offset the axis produces for idx < n
+    if (n <= 0) return 0;
+    const int idx = n - 1;
+    if (idx < a.div) return (long long)idx * a.lo;
+    return (long long)(idx / a.div) * a.hi + (long long)(a.div - 1) * a.lo;
 }
 
 struct GemmArgs {
@@ -36,95 +44,146 @@ struct GemmArgs {
     int contiguous_c;  // C is a plain row-major [M][N] array (used to zero it before a split-K overwrite)
 };
 
-constexpr int GK = 16;
-
-// TM x TN output tile per 256-thread block, GK-deep K slabs.  The next slab is fetched into registers while the
-// current one is multiplied (the contractions are small and latency-bound: K <= 5850, a few hundred CTAs at most).
-template <int TM, int TN>
-__global__ void __launch_bounds__(256) strided_gemm_kernel(const GemmArgs g) {
-    constexpr int RM = TM / 16, RN = TN / 16;              // per-thread register block
-    constexpr int LA = TM * GK / 256, LB = TN * GK / 256;  // elements each thread stages per slab
-    __shared__ float As[GK][TM + 1];
-    __shared__ float Bs[GK][TN + 1];
-    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
-    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-    float acc[RM][RN] = {};
+// fp32 GEMM over strided/composite axes: 32x32 output tile per 256-thread CTA.  The folds are many small
+// contractions (tens to a few hundred tiles, K from 52 to 5850), so the tile is small to fill the machine without
+// a cross-CTA split (the forward fold must be deterministic) and the CTA's 8 warps split every K slab four ways:
+// k-group kg = tid/64 multiplies k in [kg*GK/4, (kg+1)*GK/4) of the slab with a 4x4 register block per thread
+// (two 16-byte shared loads per 16 FMAs); the four partial tiles are summed in a fixed order at the end.
+// AKF / BKF: the operand is staged with k running fastest across a warp (8 k x 4 rows per warp: whole 32-byte
+// sectors of a k-contiguous operand, conflict-free shared stores) or with the m / n index fastest.
+constexpr int GT = 32;        // tile edge
+constexpr int GP = GT + 4;    // shared pitch (floats), keeps rows 16-byte aligned
+template <int GK, bool AKF, bool BKF>
+__global__ void __launch_bounds__(256) fold_gemm_kernel(const GemmArgs g) {
+    constexpr int L = GT * GK / 256;   // staged elements per thread per operand per slab
+    constexpr int KB = GK / 8;         // 8-wide k blocks per slab
+    constexpr int KPG = GK / 4;        // k per k-group per slab
+    __shared__ __align__(16) float As[GK][GP];
+    __shared__ __align__(16) float Bs[GK][GP];
+    __shared__ float red[3][16][64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
     const int k_begin = blockIdx.z * g.k_chunk;
     const int k_end = min(g.K, k_begin + g.k_chunk);
     const bool split = gridDim.z > 1;
-    // loop-invariant parts of the staging addresses
-    long long a_off[LA], b_off[LB];
-    int a_m[LA], a_k[LA], b_k[LB], b_n[LB];
+
+    // staging coordinates: element l of this thread is (a_k(l), a_m(l)) of the slab
+    auto st_k = [&](bool kf, int l) { return kf ? (warp % KB) * 8 + (lane & 7) : warp + 8 * l; };
+    auto st_r = [&](bool kf, int l) { return kf ? ((warp + 8 * l) / KB) * 4 + (lane >> 3) : lane; };
+    int a_off[L], b_off[L];
 #pragma unroll
-    for (int l = 0; l < LA; ++l) {
-        const int e = threadIdx.x + l * 256;
-        a_m[l] = e / GK; a_k[l] = e % GK;
-        a_off[l] = (m0 + a_m[l] < g.M) ? axis_off(g.am, m0 + a_m[l]) : -1;
+    for (int l = 0; l < L; ++l) {
+        const int m = m0 + st_r(AKF, l), n = n0 + st_r(BKF, l);
+        a_off[l] = m < g.M ? axis_off(g.am, m) : -1;
+        b_off[l] = n < g.N ? axis_off(g.bn, n) : -1;
     }
-#pragma unroll
-    for (int l = 0; l < LB; ++l) {
-        const int e = threadIdx.x + l * 256;
-        b_k[l] = e / TN; b_n[l] = e % TN;
-        b_off[l] = (n0 + b_n[l] < g.N) ? axis_off(g.bn, n0 + b_n[l]) : -1;
-    }
-    float ra[LA], rb[LB];
+    float ra[L], rb[L];
     auto fetch = [&](int k0) {
+        if (AKF) {
+            const int k = k0 + st_k(true, 0);
+            const int ko = k < k_end ? axis_off(g.ak, k) : -1;
 #pragma unroll
-        for (int l = 0; l < LA; ++l) {
-            const int k = k0 + a_k[l];
-            ra[l] = (a_off[l] >= 0 && k < k_end) ? g.A[a_off[l] + axis_off(g.ak, k)] : 0.0f;
+            for (int l = 0; l < L; ++l) ra[l] = (ko >= 0 && a_off[l] >= 0) ? __ldg(g.A + a_off[l] + ko) : 0.0f;
+        } else {
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const int k = k0 + st_k(false, l);
+                ra[l] = (k < k_end && a_off[l] >= 0) ? __ldg(g.A + a_off[l] + axis_off(g.ak, k)) : 0.0f;
+            }
         }
+        if (BKF) {
+            const int k = k0 + st_k(true, 0);
+            const int ko = k < k_end ? axis_off(g.bk, k) : -1;
 #pragma unroll
-        for (int l = 0; l < LB; ++l) {
-            const int k = k0 + b_k[l];
-            rb[l] = (b_off[l] >= 0 && k < k_end) ? g.B[axis_off(g.bk, k) + b_off[l]] : 0.0f;
+            for (int l = 0; l < L; ++l) rb[l] = (ko >= 0 && b_off[l] >= 0) ? __ldg(g.B + b_off[l] + ko) : 0.0f;
+        } else {
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const int k = k0 + st_k(false, l);
+                rb[l] = (k < k_end && b_off[l] >= 0) ? __ldg(g.B + b_off[l] + axis_off(g.bk, k)) : 0.0f;
+            }
         }
     };
+
+    const int kg = tid >> 6, t = tid & 63, tx = t & 7, ty = t >> 3;
+    float acc[4][4] = {};
     fetch(k_begin);
     for (int k0 = k_begin; k0 < k_end; k0 += GK) {
 #pragma unroll
-        for (int l = 0; l < LA; ++l) As[a_k[l]][a_m[l]] = ra[l];
-#pragma unroll
-        for (int l = 0; l < LB; ++l) Bs[b_k[l]][b_n[l]] = rb[l];
+        for (int l = 0; l < L; ++l) {
+            As[st_k(AKF, l)][st_r(AKF, l)] = ra[l];
+            Bs[st_k(BKF, l)][st_r(BKF, l)] = rb[l];
+        }
         __syncthreads();
         if (k0 + GK < k_end) fetch(k0 + GK);
 #pragma unroll
-        for (int k = 0; k < GK; ++k) {
-            float a[RM], b[RN];
+        for (int kk = 0; kk < KPG; ++kk) {
+            const int k = kg * KPG + kk;
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < RM; ++i) a[i] = As[k][ty * RM + i];
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < RN; ++j) b[j] = Bs[k][tx * RN + j];
-#pragma unroll
-            for (int i = 0; i < RM; ++i)
-#pragma unroll
-                for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
+    // fixed-order sum of the four k-group partials
+    if (kg > 0) {
 #pragma unroll
-    for (int i = 0; i < RM; ++i) {
-        const int m = m0 + ty * RM + i;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[kg - 1][i * 4 + j][t] = acc[i][j];
+    }
+    __syncthreads();
+    if (kg > 0) return;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += red[q][i * 4 + j][t];
+    int c_n[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        c_n[j] = n < g.N ? axis_off(g.cn, n) : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
         if (m >= g.M) continue;
+        float* crow = g.C + axis_off(g.cm, m);
 #pragma unroll
-        for (int j = 0; j < RN; ++j) {
-            const int n = n0 + tx * RN + j;
-            if (n >= g.N) continue;
-            float* c = g.C + axis_off(g.cm, m) + axis_off(g.cn, n);
+        for (int j = 0; j < 4; ++j) {
+            if (c_n[j] < 0) continue;
+            float* c = crow + c_n[j];
             if (split) atomicAdd(c, acc[i][j]);
             else *c = g.accumulate ? *c + acc[i][j] : acc[i][j];
         }
     }
 }
 
+template <int GK>
+static void launch_gemm_gk(const GemmArgs& g, dim3 grid, bool akf, bool bkf, cudaStream_t st) {
+    if (akf && bkf) fold_gemm_kernel<GK, true, true><<<grid, 256, 0, st>>>(g);
+    else if (akf) fold_gemm_kernel<GK, true, false><<<grid, 256, 0, st>>>(g);
+    else if (bkf) fold_gemm_kernel<GK, false, true><<<grid, 256, 0, st>>>(g);
+    else fold_gemm_kernel<GK, false, false><<<grid, 256, 0, st>>>(g);
+}
+
 // allow_split: combine split-K partials with atomics (summation order, hence the last fp32 bits, then varies
 // from run to run).  Used for gradients only; the forward fold stays deterministic so that a deploy
 // checkpoint reproduces the train-state decode bit for bit (reference main_train.py:332-349).
 static int launch_gemm(GemmArgs g, cudaStream_t st, bool allow_split = false) {
-    // 64x64 tiles when they already cover the machine, 32x32 tiles (4x the CTAs) otherwise
-    const int tiles64 = ceil_div(g.N, 64) * ceil_div(g.M, 64);
-    const int T = tiles64 >= num_sms() ? 64 : 32;
-    const int tiles = ceil_div(g.N, T) * ceil_div(g.M, T);
+    ONR_REQUIRE(axis_extent(g.am, g.M) + axis_extent(g.ak, g.K) < (1ll << 31) &&
+                axis_extent(g.bn, g.N) + axis_extent(g.bk, g.K) < (1ll << 31) &&
+                axis_extent(g.cm, g.M) + axis_extent(g.cn, g.N) < (1ll << 31),
+                "fold gemm: operand too large for 32-bit offsets");
+    // 64-deep slabs unless K would waste more than a tenth of them
+    const int GK = (long long)ceil_div(g.K, 64) * 64 * 10 <= (long long)g.K * 11 ? 64 : 32;
+    const int tiles = ceil_div(g.N, GT) * ceil_div(g.M, GT);
     int splits = 1;
     if (!g.accumulate && allow_split && g.contiguous_c && tiles < num_sms()) {
         // overwrite semantics with split-K: zero C, then accumulate partials atomically
@@ -132,17 +191,19 @@ static int launch_gemm(GemmArgs g, cudaStream_t st, bool allow_split = false) {
         g.accumulate = 1;
     }
     if (g.accumulate && allow_split) {
-        // enough CTAs to cover the machine twice, but at least 64 k-elements of work per CTA
+        // enough CTAs to cover the machine twice, but at least two slabs of work per CTA
         splits = ceil_div(2 * num_sms(), tiles);
-        const int max_splits = ceil_div(g.K, 64);
+        const int max_splits = ceil_div(g.K, 2 * GK);
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
     }
     g.k_chunk = ceil_div(ceil_div(g.K, splits), GK) * GK;
     splits = ceil_div(g.K, g.k_chunk);
-    dim3 grid(ceil_div(g.N, T), ceil_div(g.M, T), splits);
-    if (T == 64) strided_gemm_kernel<64, 64><<<grid, 256, 0, st>>>(g);
-    else strided_gemm_kernel<32, 32><<<grid, 256, 0, st>>>(g);
+    dim3 grid(ceil_div(g.N, GT), ceil_div(g.M, GT), splits);
+    // stage an operand k-fastest when its k stride is 1 (composite axes: when the inner run is contiguous)
+    const bool akf = g.ak.lo == 1, bkf = g.bk.lo == 1;
+    if (GK == 64) launch_gemm_gk<64>(g, grid, akf, bkf, st);
+    else launch_gemm_gk<32>(g, grid, akf, bkf, st);
     ONR_LAUNCH_CHECK();
     return 0;
 }

@@ -8,44 +8,90 @@
 namespace onr {
 
 constexpr int kHeadMaxC = 128;
+constexpr int kHeadMaxChunks = kHeadMaxC / 8;
 
-__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ y, size_t npix, int HW, int C, int Cp,
-                                const float* __restrict__ Wh, const float* __restrict__ bh, int use_sigmoid,
-                                float* __restrict__ img) {
-    __shared__ float sw[3 * kHeadMaxC];
-    for (int i = threadIdx.x; i < 3 * Cp; i += blockDim.x) {
-        const int k = i / Cp, c = i % Cp;
-        sw[i] = c < C ? Wh[k * C + c] : 0.0f;
-    }
-    __syncthreads();
-    const float b0 = bh[0], b1 = bh[1], b2 = bh[2];
+// Every kernel here gives a thread one fixed 8-channel piece (ch = tid % chunks) of a pixel that advances by a
+// whole number of block-sized pixel groups, so the head weights of that piece live in registers, consecutive
+// threads read consecutive 16-byte pieces, and the inner loops carry no division (all indices are 32-bit: the host
+// wrappers reject npix * chunks >= 2^31).
+__device__ __forceinline__ void head_load_w(const float* __restrict__ Wh, int C, int ch, float w[3][8]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = ch * 8 + e;
+            w[k][e] = c < C ? __ldg(Wh + k * C + c) : 0.0f;
+        }
+}
+
+__device__ __forceinline__ uint32_t head_img_offset(uint32_t pix, uint32_t HW) {
+    uint32_t b = 0, hw = pix;
+    if (pix >= HW) { b = pix / HW; hw = pix - b * HW; }   // batch 1 (the training case) never divides
+    return b * 3u * HW + hw;
+}
+
+__device__ __forceinline__ float head_act(float a, int use_sigmoid) {
+    return use_sigmoid ? 1.0f / (1.0f + expf(-a)) : (tanhf(a) + 1.0f) * 0.5f;
+}
+
+// blockDim.x = ppb * chunks.  Each pass covers kFwdU groups of ppb pixels: every thread reduces its 8 channels of
+// one pixel per group against the three weight rows, the `chunks` partials of a pixel meet in shared memory
+// (double-buffered: one barrier per pass), and the first 3*ppb threads finish the pixels and write the planar fp32
+// image with unit stride.  The next pass's activations are already in flight while the current one is reduced.
+constexpr int kFwdU = 2;
+__global__ void __launch_bounds__(512)
+head_fwd_kernel(const __nv_bfloat16* __restrict__ y, uint32_t npix, uint32_t HW, int C, int Cp,
+                const float* __restrict__ Wh, const float* __restrict__ bh, int use_sigmoid,
+                float* __restrict__ img) {
+    __shared__ float part[2][kFwdU][3][512 + 512 / 4];   // [buf][u][k][pl * (chunks + 1) + ch]
     const int chunks = Cp / 8;
-    for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < npix;
-         pix += (size_t)gridDim.x * blockDim.x) {
-        const uint4* yp = reinterpret_cast<const uint4*>(y + pix * Cp);
-        float a0 = b0, a1 = b1, a2 = b2;
-        for (int ch = 0; ch < chunks; ++ch) {
-            const uint4 v = __ldg(yp + ch);
-            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    const int ppb = blockDim.x / chunks;
+    const int pl = threadIdx.x / chunks, ch = threadIdx.x - pl * chunks;
+    float w[3][8];
+    head_load_w(Wh, C, ch, w);
+    const int fk = threadIdx.x / ppb, fp = threadIdx.x - fk * ppb;   // finishing role: channel fk of pixel fp
+    const float fb = fk < 3 ? __ldg(bh + fk) : 0.0f;
+    const uint32_t span = kFwdU * ppb, step = gridDim.x * span;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    auto load = [&](uint32_t base, uint4 v[kFwdU]) {
+#pragma unroll
+        for (int u = 0; u < kFwdU; ++u) {
+            const uint32_t pix = base + u * ppb + pl;
+            v[u] = (base < npix && pix < npix) ? __ldg(reinterpret_cast<const uint4*>(y) + pix * chunks + ch) : zero;
+        }
+    };
+    uint4 nxt[kFwdU];
+    load(blockIdx.x * span, nxt);
+    int buf = 0;
+    for (uint32_t base = blockIdx.x * span; base < npix; base += step, buf ^= 1) {
+        uint4 cur[kFwdU];
+#pragma unroll
+        for (int u = 0; u < kFwdU; ++u) cur[u] = nxt[u];
+        load(base + step, nxt);
+#pragma unroll
+        for (int u = 0; u < kFwdU; ++u) {
+            const uint32_t q[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+            float a[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float lo = bf16_lo(u[e]), hi = bf16_hi(u[e]);
-                const int c = ch * 8 + e * 2;
-                a0 = fmaf(lo, sw[c], a0);           a0 = fmaf(hi, sw[c + 1], a0);
-                a1 = fmaf(lo, sw[Cp + c], a1);      a1 = fmaf(hi, sw[Cp + c + 1], a1);
-                a2 = fmaf(lo, sw[2 * Cp + c], a2);  a2 = fmaf(hi, sw[2 * Cp + c + 1], a2);
+                const float lo = bf16_lo(q[e]), hi = bf16_hi(q[e]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) a[k] = fmaf(hi, w[k][2 * e + 1], fmaf(lo, w[k][2 * e], a[k]));
             }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) part[buf][u][k][pl * (chunks + 1) + ch] = a[k];
         }
-        const size_t b = pix / HW, hw = pix % HW;
-        float* o = img + b * 3 * (size_t)HW + hw;
-        if (use_sigmoid) {
-            o[0] = 1.0f / (1.0f + expf(-a0));
-            o[HW] = 1.0f / (1.0f + expf(-a1));
-            o[2 * (size_t)HW] = 1.0f / (1.0f + expf(-a2));
-        } else {
-            o[0] = (tanhf(a0) + 1.0f) * 0.5f;
-            o[HW] = (tanhf(a1) + 1.0f) * 0.5f;
-            o[2 * (size_t)HW] = (tanhf(a2) + 1.0f) * 0.5f;
+        __syncthreads();
+        if (fk < 3) {
+#pragma unroll
+            for (int u = 0; u < kFwdU; ++u) {
+                const uint32_t pix = base + u * ppb + fp;
+                if (pix >= npix) continue;
+                float s = fb;
+                const float* pp = &part[buf][u][fk][fp * (chunks + 1)];
+                for (int c = 0; c < chunks; ++c) s += pp[c];
+                img[head_img_offset(pix, HW) + fk * HW] = head_act(s, use_sigmoid);
+            }
         }
     }
 }
@@ -55,95 +101,89 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ y, size_t npix
 //   g_pre[k] = gimg[k] * d(act)/d(pre)  with  (tanh+1)/2 -> 2 o (1-o),  sigmoid -> o (1-o)
 //   dz[px, c]  = (sum_k g_pre[k] Wh[k, c]) * SiLU'(z)[px, c]
 //   gWh[k, c] += sum_px g_pre[k] y[px, c] ;  gbh[k] += sum_px g_pre[k]
-// Thread layout for both: 8-channel (16-byte) pieces, (Cp/8) consecutive threads per pixel.
-__device__ __forceinline__ void head_gpre(const float* __restrict__ gimg, const float* __restrict__ img, size_t pix,
-                                          int HW, int use_sigmoid, float gp[3]) {
-    const size_t b = pix / HW, hw = pix % HW;
-    const size_t io = b * 3 * (size_t)HW + hw;
+__device__ __forceinline__ void head_gpre(const float* __restrict__ gimg, const float* __restrict__ img,
+                                          uint32_t pix, uint32_t HW, int use_sigmoid, float gp[3]) {
+    const uint32_t io = head_img_offset(pix, HW);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float o = __ldg(img + io + k * (size_t)HW);
-        const float g = __ldg(gimg + io + k * (size_t)HW);
+        const float o = __ldg(img + io + k * HW);
+        const float g = __ldg(gimg + io + k * HW);
         gp[k] = use_sigmoid ? g * o * (1.0f - o) : g * 2.0f * o * (1.0f - o);
     }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kDzUnroll = 4;   // independent 16-byte loads in flight per thread
+
+__global__ void __launch_bounds__(512)
 head_bwd_dz_kernel(const float* __restrict__ gimg, const float* __restrict__ img,
-                   const __nv_bfloat16* __restrict__ dsilu, size_t npix, int HW, int C, int Cp,
+                   const __nv_bfloat16* __restrict__ dsilu, uint32_t npix, uint32_t HW, int C, int Cp,
                    const float* __restrict__ Wh, int use_sigmoid, __nv_bfloat16* __restrict__ dz) {
-    __shared__ float sw[3 * kHeadMaxC];
-    for (int i = threadIdx.x; i < 3 * Cp; i += blockDim.x) {
-        const int k = i / Cp, c = i % Cp;
-        sw[i] = c < C ? Wh[k * C + c] : 0.0f;
-    }
-    __syncthreads();
     const int chunks = Cp / 8;
-    const size_t total = npix * chunks;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    // 4 independent 16-byte loads in flight per thread
-    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
-        uint4 dv[4];
-        float gp[4][3];
+    const int ppb = blockDim.x / chunks;
+    const int pl = threadIdx.x / chunks, ch = threadIdx.x - pl * chunks;
+    float w[3][8];
+    head_load_w(Wh, C, ch, w);
+    const uint32_t step = gridDim.x * ppb;
+    for (uint32_t pix0 = blockIdx.x * ppb + pl; pix0 < npix; pix0 += kDzUnroll * step) {
+        uint4 dv[kDzUnroll];
+        float gp[kDzUnroll][3];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const size_t i = i0 + u * stride;
-            if (i < total) {
-                dv[u] = __ldg(reinterpret_cast<const uint4*>(dsilu) + i);
-                head_gpre(gimg, img, i / chunks, HW, use_sigmoid, gp[u]);
+        for (int u = 0; u < kDzUnroll; ++u) {
+            const uint32_t pix = pix0 + u * step;
+            if (pix < npix) {
+                dv[u] = __ldg(reinterpret_cast<const uint4*>(dsilu) + pix * chunks + ch);
+                head_gpre(gimg, img, pix, HW, use_sigmoid, gp[u]);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const size_t i = i0 + u * stride;
-            if (i >= total) continue;
-            const int ch = (int)(i % chunks);
+        for (int u = 0; u < kDzUnroll; ++u) {
+            const uint32_t pix = pix0 + u * step;
+            if (pix >= npix) continue;
             const uint32_t du[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
             uint32_t out[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int c = ch * 8 + e * 2;
                 float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    d0 = fmaf(gp[u][k], sw[k * Cp + c], d0);
-                    d1 = fmaf(gp[u][k], sw[k * Cp + c + 1], d1);
+                    d0 = fmaf(gp[u][k], w[k][2 * e], d0);
+                    d1 = fmaf(gp[u][k], w[k][2 * e + 1], d1);
                 }
                 out[e] = pack_bf16x2(d0 * bf16_lo(du[e]), d1 * bf16_hi(du[e]));
             }
-            reinterpret_cast<uint4*>(dz)[i] = make_uint4(out[0], out[1], out[2], out[3]);
+            reinterpret_cast<uint4*>(dz)[pix * chunks + ch] = make_uint4(out[0], out[1], out[2], out[3]);
         }
     }
 }
 
 // blockDim.x = chunks * lanes; thread (lane, ch) walks pixels lane, lane + lanes*gridDim, ... for its 8 channels.
 __global__ void head_bwd_gw_kernel(const float* __restrict__ gimg, const float* __restrict__ img,
-                                   const __nv_bfloat16* __restrict__ y, size_t npix, int HW, int C, int Cp,
+                                   const __nv_bfloat16* __restrict__ y, uint32_t npix, uint32_t HW, int C, int Cp,
                                    int use_sigmoid, float* __restrict__ gWh, float* __restrict__ gbh) {
     __shared__ float sg[3 * kHeadMaxC + 3];
     for (int i = threadIdx.x; i < 3 * Cp + 3; i += blockDim.x) sg[i] = 0.0f;
     __syncthreads();
     const int chunks = Cp / 8;
     const int lanes = blockDim.x / chunks;
-    const int ch = threadIdx.x % chunks, lane = threadIdx.x / chunks;
+    const int lane = threadIdx.x / chunks, ch = threadIdx.x - lane * chunks;
     float gw[3][8];
     float gb[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int e = 0; e < 8; ++e) gw[k][e] = 0.0f;
-    if (lane < lanes) {
-        const size_t stride = (size_t)gridDim.x * lanes;
-        for (size_t pix0 = (size_t)blockIdx.x * lanes + lane; pix0 < npix; pix0 += 2 * stride) {
+    {
+        const uint32_t stride = gridDim.x * lanes;
+        for (uint32_t pix0 = blockIdx.x * lanes + lane; pix0 < npix; pix0 += 2 * stride) {
             uint4 yv[2];
             float gp[2][3];
             bool ok[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const size_t pix = pix0 + u * stride;
+                const uint32_t pix = pix0 + u * stride;
                 ok[u] = pix < npix;
                 if (ok[u]) {
-                    yv[u] = __ldg(reinterpret_cast<const uint4*>(y + pix * Cp) + ch);
+                    yv[u] = __ldg(reinterpret_cast<const uint4*>(y) + pix * chunks + ch);
                     head_gpre(gimg, img, pix, HW, use_sigmoid, gp[u]);
                 }
             }
@@ -182,6 +222,10 @@ __global__ void head_bwd_gw_kernel(const float* __restrict__ gimg, const float* 
     if (threadIdx.x < 3) atomicAdd(&gbh[threadIdx.x], sg[3 * Cp + threadIdx.x]);
 }
 
+// threads per block: a multiple of `chunks` close to `target`, holding whole pixels
+static inline int head_threads(int chunks, int target) { return (target / chunks) * chunks; }
+static inline bool head_fits_u32(size_t npix, int chunks) { return npix * (size_t)chunks * 3 < (1ull << 31); }
+
 }  // namespace onr
 
 extern "C" {
@@ -191,10 +235,16 @@ int onr_head_fwd(const void* y, int B, int H, int W, int C, int Cp, const float*
     using namespace onr;
     ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
     const size_t npix = (size_t)B * H * W;
-    int grid = (int)((npix + 255) / 256);
-    if (grid > num_sms() * 16) grid = num_sms() * 16;
-    head_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(y), npix,
-                                                           H * W, C, Cp, Wh, bh, use_sigmoid, img);
+    const int chunks = Cp / 8;
+    ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
+    const int threads = head_threads(chunks, 384);
+    const int ppb = threads / chunks;
+    ONR_REQUIRE(3 * ppb <= threads, "head: block too small to finish its pixels");
+    int grid = (int)((npix + (size_t)ppb * kFwdU - 1) / ((size_t)ppb * kFwdU));
+    if (grid > num_sms() * 4) grid = num_sms() * 4;
+    head_fwd_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(y),
+                                                               (uint32_t)npix, (uint32_t)(H * W), C, Cp, Wh, bh,
+                                                               use_sigmoid, img);
     ONR_LAUNCH_CHECK();
     return 0;
 }
@@ -204,12 +254,15 @@ int onr_head_bwd_dz(const float* gimg, const float* img, const void* dsilu, int 
     using namespace onr;
     ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
     const size_t npix = (size_t)B * H * W;
-    const size_t total = npix * (Cp / 8);
-    size_t grid = (total + 256 * 4 - 1) / (256 * 4);
+    const int chunks = Cp / 8;
+    ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
+    const int threads = head_threads(chunks, 256);
+    const int ppb = threads / chunks;
+    size_t grid = (npix + (size_t)ppb * kDzUnroll - 1) / ((size_t)ppb * kDzUnroll);
     if (grid > (size_t)num_sms() * 8) grid = (size_t)num_sms() * 8;
-    head_bwd_dz_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(
-        gimg, img, reinterpret_cast<const __nv_bfloat16*>(dsilu), npix, H * W, C, Cp, Wh, use_sigmoid,
-        reinterpret_cast<__nv_bfloat16*>(dz));
+    head_bwd_dz_kernel<<<(int)grid, threads, 0, (cudaStream_t)stream>>>(
+        gimg, img, reinterpret_cast<const __nv_bfloat16*>(dsilu), (uint32_t)npix, (uint32_t)(H * W), C, Cp, Wh,
+        use_sigmoid, reinterpret_cast<__nv_bfloat16*>(dz));
     ONR_LAUNCH_CHECK();
     return 0;
 }
@@ -220,12 +273,14 @@ int onr_head_bwd_gw(const float* gimg, const float* img, const void* y, int B, i
     ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
     const size_t npix = (size_t)B * H * W;
     const int chunks = Cp / 8;
+    ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
     const int lanes = 384 / chunks;
     const int threads = lanes * chunks;
     int grid = (int)((npix + lanes - 1) / lanes);
     if (grid > num_sms() * 4) grid = num_sms() * 4;
     head_bwd_gw_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
-        gimg, img, reinterpret_cast<const __nv_bfloat16*>(y), npix, H * W, C, Cp, use_sigmoid, gWh, gbh);
+        gimg, img, reinterpret_cast<const __nv_bfloat16*>(y), (uint32_t)npix, (uint32_t)(H * W), C, Cp,
+        use_sigmoid, gWh, gbh);
     ONR_LAUNCH_CHECK();
     return 0;
 }

@@ -135,6 +135,55 @@ __global__ void stem_bwd_layer2_kernel(const __nv_bfloat16* __restrict__ g0, int
     }
 }
 
+// Batch-1 fast path (the training configuration): hid % 4 == 0, gradients are plain read-modify-writes.  Thread t owns
+// the four hidden units 4t..4t+3 (+512 per extra pass); a block owns kStemFastRows output rows, all of whose W2 /
+// gW2 rows are in flight at once (the kernel moves 3 x n_out x hid floats and nothing else of size).
+constexpr int kStemFastRows = 8;
+constexpr int kStemFastU = 2;   // hid <= 128 * 4 * kStemFastU
+__global__ void __launch_bounds__(128)
+stem_bwd_layer2_b1_kernel(const __nv_bfloat16* __restrict__ g0, const float* __restrict__ h1, int hid,
+                          const float* __restrict__ W2, int fc_dim, int fh, int fw, int Cp,
+                          float* __restrict__ gW2, float* __restrict__ gb2, float* __restrict__ dh1) {
+    const int n_out = fc_dim * fh * fw, HW = fh * fw;
+    const int o_begin = blockIdx.x * kStemFastRows;
+    float g[kStemFastRows];
+#pragma unroll
+    for (int r = 0; r < kStemFastRows; ++r) {
+        const int o = o_begin + r;
+        g[r] = 0.0f;
+        if (o < n_out) {
+            const int c = o / HW, hw = o - c * HW;
+            g[r] = __bfloat162float(g0[(size_t)hw * Cp + c]);
+        }
+    }
+    if (threadIdx.x < kStemFastRows && o_begin + threadIdx.x < n_out) gb2[o_begin + threadIdx.x] += g[threadIdx.x];
+#pragma unroll
+    for (int u = 0; u < kStemFastU; ++u) {
+        const int j = (threadIdx.x + u * 128) * 4;
+        if (j >= hid) break;
+        const float4 h = *reinterpret_cast<const float4*>(h1 + j);
+        float4 w[kStemFastRows], gwv[kStemFastRows];
+#pragma unroll
+        for (int r = 0; r < kStemFastRows; ++r) {
+            const size_t idx = (size_t)min(o_begin + r, n_out - 1) * hid + j;
+            w[r] = __ldg(reinterpret_cast<const float4*>(W2 + idx));
+            gwv[r] = *reinterpret_cast<const float4*>(gW2 + idx);
+        }
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int r = 0; r < kStemFastRows; ++r) {
+            if (o_begin + r >= n_out) break;
+            acc.x = fmaf(w[r].x, g[r], acc.x); acc.y = fmaf(w[r].y, g[r], acc.y);
+            acc.z = fmaf(w[r].z, g[r], acc.z); acc.w = fmaf(w[r].w, g[r], acc.w);
+            gwv[r].x = fmaf(g[r], h.x, gwv[r].x); gwv[r].y = fmaf(g[r], h.y, gwv[r].y);
+            gwv[r].z = fmaf(g[r], h.z, gwv[r].z); gwv[r].w = fmaf(g[r], h.w, gwv[r].w);
+            *reinterpret_cast<float4*>(gW2 + (size_t)(o_begin + r) * hid + j) = gwv[r];
+        }
+        atomicAdd(&dh1[j], acc.x); atomicAdd(&dh1[j + 1], acc.y);
+        atomicAdd(&dh1[j + 2], acc.z); atomicAdd(&dh1[j + 3], acc.w);
+    }
+}
+
 __global__ void stem_bwd_layer1_kernel(const float* __restrict__ dh1, const float* __restrict__ pre1,
                                        const float* __restrict__ embed, int B, int hid, int E,
                                        float* __restrict__ gW1, float* __restrict__ gb1) {
@@ -196,9 +245,14 @@ int onr_stem_bwd(const void* g0, int B, const float* embed, int emb_len, const f
     cudaStream_t st = (cudaStream_t)stream;
     ONR_CUDA(cudaMemsetAsync(scratch_dh1, 0, (size_t)B * hid * sizeof(float), st));
     const int n_out = fc_dim * fh * fw;
-    dim3 grid(ceil_div(n_out, kStemRows), B);
-    stem_bwd_layer2_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g0), B, h1, hid, W2,
-                                                 fc_dim, fh, fw, Cp, gW2, gb2, scratch_dh1);
+    if (B == 1 && hid % 4 == 0 && hid <= 128 * 4 * kStemFastU) {
+        stem_bwd_layer2_b1_kernel<<<ceil_div(n_out, kStemFastRows), 128, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(g0), h1, hid, W2, fc_dim, fh, fw, Cp, gW2, gb2, scratch_dh1);
+    } else {
+        dim3 grid(ceil_div(n_out, kStemRows), B);
+        stem_bwd_layer2_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g0), B, h1, hid, W2,
+                                                     fc_dim, fh, fw, Cp, gW2, gb2, scratch_dh1);
+    }
     ONR_LAUNCH_CHECK();
     stem_bwd_layer1_kernel<<<ceil_div(hid * emb_len, 256), 256, 0, st>>>(scratch_dh1, pre1, embed, B, hid,
                                                                         emb_len, gW1, gb1);
