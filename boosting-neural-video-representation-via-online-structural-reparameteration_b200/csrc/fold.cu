@@ -53,7 +53,8 @@ struct GemmArgs {
 // sectors of a k-contiguous operand, conflict-free shared stores) or with the m / n index fastest.
 constexpr int GT = 32;        // tile edge
 constexpr int GP = GT + 4;    // shared pitch (floats), keeps rows 16-byte aligned
-template <int GK, bool AKF, bool BKF>
+// SK: both k axes are plain strides (all contractions but gW1), so the slab loop carries no axis decomposition.
+template <int GK, bool AKF, bool BKF, bool SK>
 __global__ void __launch_bounds__(256) fold_gemm_kernel(const GemmArgs g) {
     constexpr int L = GT * GK / 256;   // staged elements per thread per operand per slab
     constexpr int KB = GK / 8;         // 8-wide k blocks per slab
@@ -78,29 +79,32 @@ __global__ void __launch_bounds__(256) fold_gemm_kernel(const GemmArgs g) {
         b_off[l] = n < g.N ? axis_off(g.bn, n) : -1;
     }
     float ra[L], rb[L];
+    const int ak_lo = (int)g.ak.lo, bk_lo = (int)g.bk.lo;
+    auto k_off_a = [&](int k) { return SK ? k * ak_lo : axis_off(g.ak, k); };
+    auto k_off_b = [&](int k) { return SK ? k * bk_lo : axis_off(g.bk, k); };
     auto fetch = [&](int k0) {
         if (AKF) {
             const int k = k0 + st_k(true, 0);
-            const int ko = k < k_end ? axis_off(g.ak, k) : -1;
+            const int ko = k < k_end ? k_off_a(k) : -1;
 #pragma unroll
             for (int l = 0; l < L; ++l) ra[l] = (ko >= 0 && a_off[l] >= 0) ? __ldg(g.A + a_off[l] + ko) : 0.0f;
         } else {
 #pragma unroll
             for (int l = 0; l < L; ++l) {
                 const int k = k0 + st_k(false, l);
-                ra[l] = (k < k_end && a_off[l] >= 0) ? __ldg(g.A + a_off[l] + axis_off(g.ak, k)) : 0.0f;
+                ra[l] = (k < k_end && a_off[l] >= 0) ? __ldg(g.A + a_off[l] + k_off_a(k)) : 0.0f;
             }
         }
         if (BKF) {
             const int k = k0 + st_k(true, 0);
-            const int ko = k < k_end ? axis_off(g.bk, k) : -1;
+            const int ko = k < k_end ? k_off_b(k) : -1;
 #pragma unroll
             for (int l = 0; l < L; ++l) rb[l] = (ko >= 0 && b_off[l] >= 0) ? __ldg(g.B + b_off[l] + ko) : 0.0f;
         } else {
 #pragma unroll
             for (int l = 0; l < L; ++l) {
                 const int k = k0 + st_k(false, l);
-                rb[l] = (k < k_end && b_off[l] >= 0) ? __ldg(g.B + b_off[l] + axis_off(g.bk, k)) : 0.0f;
+                rb[l] = (k < k_end && b_off[l] >= 0) ? __ldg(g.B + b_off[l] + k_off_b(k)) : 0.0f;
             }
         }
     };
@@ -165,12 +169,12 @@ __global__ void __launch_bounds__(256) fold_gemm_kernel(const GemmArgs g) {
     }
 }
 
-template <int GK>
+template <int GK, bool SK>
 static void launch_gemm_gk(const GemmArgs& g, dim3 grid, bool akf, bool bkf, cudaStream_t st) {
-    if (akf && bkf) fold_gemm_kernel<GK, true, true><<<grid, 256, 0, st>>>(g);
-    else if (akf) fold_gemm_kernel<GK, true, false><<<grid, 256, 0, st>>>(g);
-    else if (bkf) fold_gemm_kernel<GK, false, true><<<grid, 256, 0, st>>>(g);
-    else fold_gemm_kernel<GK, false, false><<<grid, 256, 0, st>>>(g);
+    if (akf && bkf) fold_gemm_kernel<GK, true, true, SK><<<grid, 256, 0, st>>>(g);
+    else if (akf) fold_gemm_kernel<GK, true, false, SK><<<grid, 256, 0, st>>>(g);
+    else if (bkf) fold_gemm_kernel<GK, false, true, SK><<<grid, 256, 0, st>>>(g);
+    else fold_gemm_kernel<GK, false, false, SK><<<grid, 256, 0, st>>>(g);
 }
 
 // allow_split: combine split-K partials with atomics (summation order, hence the last fp32 bits, then varies
@@ -202,8 +206,11 @@ static int launch_gemm(GemmArgs g, cudaStream_t st, bool allow_split = false) {
     dim3 grid(ceil_div(g.N, GT), ceil_div(g.M, GT), splits);
     // stage an operand k-fastest when its k stride is 1 (composite axes: when the inner run is contiguous)
     const bool akf = g.ak.lo == 1, bkf = g.bk.lo == 1;
-    if (GK == 64) launch_gemm_gk<64>(g, grid, akf, bkf, st);
-    else launch_gemm_gk<32>(g, grid, akf, bkf, st);
+    const bool sk = g.ak.div >= g.K && g.bk.div >= g.K;
+    if (GK == 64 && sk) launch_gemm_gk<64, true>(g, grid, akf, bkf, st);
+    else if (GK == 64) launch_gemm_gk<64, false>(g, grid, akf, bkf, st);
+    else if (sk) launch_gemm_gk<32, true>(g, grid, akf, bkf, st);
+    else launch_gemm_gk<32, false>(g, grid, akf, bkf, st);
     ONR_LAUNCH_CHECK();
     return 0;
 }

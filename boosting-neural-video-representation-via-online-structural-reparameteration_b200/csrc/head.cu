@@ -24,10 +24,13 @@ __device__ __forceinline__ void head_load_w(const float* __restrict__ Wh, int C,
         }
 }
 
+// kOne: a single image (batch 1, the training case) needs no division, which also keeps the loops free of branches
+// so that every load of an unrolled pass is issued before the first use.
+template <bool kOne>
 __device__ __forceinline__ uint32_t head_img_offset(uint32_t pix, uint32_t HW) {
-    uint32_t b = 0, hw = pix;
-    if (pix >= HW) { b = pix / HW; hw = pix - b * HW; }   // batch 1 (the training case) never divides
-    return b * 3u * HW + hw;
+    if (kOne) return pix;
+    const uint32_t b = pix / HW;
+    return b * 3u * HW + (pix - b * HW);
 }
 
 __device__ __forceinline__ float head_act(float a, int use_sigmoid) {
@@ -39,6 +42,7 @@ __device__ __forceinline__ float head_act(float a, int use_sigmoid) {
 // (double-buffered: one barrier per pass), and the first 3*ppb threads finish the pixels and write the planar fp32
 // image with unit stride.  The next pass's activations are already in flight while the current one is reduced.
 constexpr int kFwdU = 2;
+template <bool kOne>
 __global__ void __launch_bounds__(512)
 head_fwd_kernel(const __nv_bfloat16* __restrict__ y, uint32_t npix, uint32_t HW, int C, int Cp,
                 const float* __restrict__ Wh, const float* __restrict__ bh, int use_sigmoid,
@@ -90,7 +94,7 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ y, uint32_t npix, uint32_t HW,
                 float s = fb;
                 const float* pp = &part[buf][u][fk][fp * (chunks + 1)];
                 for (int c = 0; c < chunks; ++c) s += pp[c];
-                img[head_img_offset(pix, HW) + fk * HW] = head_act(s, use_sigmoid);
+                img[head_img_offset<kOne>(pix, HW) + fk * HW] = head_act(s, use_sigmoid);
             }
         }
     }
@@ -101,9 +105,10 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ y, uint32_t npix, uint32_t HW,
 //   g_pre[k] = gimg[k] * d(act)/d(pre)  with  (tanh+1)/2 -> 2 o (1-o),  sigmoid -> o (1-o)
 //   dz[px, c]  = (sum_k g_pre[k] Wh[k, c]) * SiLU'(z)[px, c]
 //   gWh[k, c] += sum_px g_pre[k] y[px, c] ;  gbh[k] += sum_px g_pre[k]
+template <bool kOne>
 __device__ __forceinline__ void head_gpre(const float* __restrict__ gimg, const float* __restrict__ img,
                                           uint32_t pix, uint32_t HW, int use_sigmoid, float gp[3]) {
-    const uint32_t io = head_img_offset(pix, HW);
+    const uint32_t io = head_img_offset<kOne>(pix, HW);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float o = __ldg(img + io + k * HW);
@@ -113,8 +118,10 @@ __device__ __forceinline__ void head_gpre(const float* __restrict__ gimg, const 
 }
 
 constexpr int kDzUnroll = 4;   // independent 16-byte loads in flight per thread
+constexpr int kGwUnroll = 4;
 
-__global__ void __launch_bounds__(512)
+template <bool kOne>
+__global__ void __launch_bounds__(256, 4)
 head_bwd_dz_kernel(const float* __restrict__ gimg, const float* __restrict__ img,
                    const __nv_bfloat16* __restrict__ dsilu, uint32_t npix, uint32_t HW, int C, int Cp,
                    const float* __restrict__ Wh, int use_sigmoid, __nv_bfloat16* __restrict__ dz) {
@@ -127,18 +134,16 @@ head_bwd_dz_kernel(const float* __restrict__ gimg, const float* __restrict__ img
     for (uint32_t pix0 = blockIdx.x * ppb + pl; pix0 < npix; pix0 += kDzUnroll * step) {
         uint4 dv[kDzUnroll];
         float gp[kDzUnroll][3];
+        // out-of-range members of the pass re-read pixel pix0 (loads stay unconditional), their stores are skipped
 #pragma unroll
         for (int u = 0; u < kDzUnroll; ++u) {
-            const uint32_t pix = pix0 + u * step;
-            if (pix < npix) {
-                dv[u] = __ldg(reinterpret_cast<const uint4*>(dsilu) + pix * chunks + ch);
-                head_gpre(gimg, img, pix, HW, use_sigmoid, gp[u]);
-            }
+            const uint32_t pix = pix0 + u * step < npix ? pix0 + u * step : pix0;
+            dv[u] = __ldg(reinterpret_cast<const uint4*>(dsilu) + pix * chunks + ch);
+            head_gpre<kOne>(gimg, img, pix, HW, use_sigmoid, gp[u]);
         }
 #pragma unroll
         for (int u = 0; u < kDzUnroll; ++u) {
             const uint32_t pix = pix0 + u * step;
-            if (pix >= npix) continue;
             const uint32_t du[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
             uint32_t out[4];
 #pragma unroll
@@ -151,13 +156,16 @@ head_bwd_dz_kernel(const float* __restrict__ gimg, const float* __restrict__ img
                 }
                 out[e] = pack_bf16x2(d0 * bf16_lo(du[e]), d1 * bf16_hi(du[e]));
             }
-            reinterpret_cast<uint4*>(dz)[pix * chunks + ch] = make_uint4(out[0], out[1], out[2], out[3]);
+            if (pix < npix)
+                reinterpret_cast<uint4*>(dz)[pix * chunks + ch] = make_uint4(out[0], out[1], out[2], out[3]);
         }
     }
 }
 
 // blockDim.x = chunks * lanes; thread (lane, ch) walks pixels lane, lane + lanes*gridDim, ... for its 8 channels.
-__global__ void head_bwd_gw_kernel(const float* __restrict__ gimg, const float* __restrict__ img,
+template <bool kOne>
+__global__ void __launch_bounds__(384)
+head_bwd_gw_kernel(const float* __restrict__ gimg, const float* __restrict__ img,
                                    const __nv_bfloat16* __restrict__ y, uint32_t npix, uint32_t HW, int C, int Cp,
                                    int use_sigmoid, float* __restrict__ gWh, float* __restrict__ gbh) {
     __shared__ float sg[3 * kHeadMaxC + 3];
@@ -174,22 +182,19 @@ __global__ void head_bwd_gw_kernel(const float* __restrict__ gimg, const float* 
         for (int e = 0; e < 8; ++e) gw[k][e] = 0.0f;
     {
         const uint32_t stride = gridDim.x * lanes;
-        for (uint32_t pix0 = blockIdx.x * lanes + lane; pix0 < npix; pix0 += 2 * stride) {
-            uint4 yv[2];
-            float gp[2][3];
-            bool ok[2];
+        for (uint32_t pix0 = blockIdx.x * lanes + lane; pix0 < npix; pix0 += kGwUnroll * stride) {
+            uint4 yv[kGwUnroll];
+            float gp[kGwUnroll][3];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const uint32_t pix = pix0 + u * stride;
-                ok[u] = pix < npix;
-                if (ok[u]) {
-                    yv[u] = __ldg(reinterpret_cast<const uint4*>(y) + pix * chunks + ch);
-                    head_gpre(gimg, img, pix, HW, use_sigmoid, gp[u]);
-                }
+            for (int u = 0; u < kGwUnroll; ++u) {
+                const bool ok = pix0 + u * stride < npix;
+                const uint32_t pix = ok ? pix0 + u * stride : pix0;
+                yv[u] = __ldg(reinterpret_cast<const uint4*>(y) + pix * chunks + ch);
+                head_gpre<kOne>(gimg, img, pix, HW, use_sigmoid, gp[u]);
+                if (!ok) gp[u][0] = gp[u][1] = gp[u][2] = 0.0f;   // contributes nothing
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (!ok[u]) continue;
+            for (int u = 0; u < kGwUnroll; ++u) {
                 const uint32_t yu[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -200,11 +205,9 @@ __global__ void head_bwd_gw_kernel(const float* __restrict__ gimg, const float* 
                         gw[k][e * 2 + 1] = fmaf(gp[u][k], y1, gw[k][e * 2 + 1]);
                     }
                 }
-                if (ch == 0) {
-                    gb[0] += gp[u][0];
-                    gb[1] += gp[u][1];
-                    gb[2] += gp[u][2];
-                }
+                gb[0] += gp[u][0];
+                gb[1] += gp[u][1];
+                gb[2] += gp[u][2];
             }
         }
 #pragma unroll
@@ -242,9 +245,9 @@ int onr_head_fwd(const void* y, int B, int H, int W, int C, int Cp, const float*
     ONR_REQUIRE(3 * ppb <= threads, "head: block too small to finish its pixels");
     int grid = (int)((npix + (size_t)ppb * kFwdU - 1) / ((size_t)ppb * kFwdU));
     if (grid > num_sms() * 4) grid = num_sms() * 4;
-    head_fwd_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(y),
-                                                               (uint32_t)npix, (uint32_t)(H * W), C, Cp, Wh, bh,
-                                                               use_sigmoid, img);
+    auto kern = B == 1 ? head_fwd_kernel<true> : head_fwd_kernel<false>;
+    kern<<<grid, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(y), (uint32_t)npix,
+                                                    (uint32_t)(H * W), C, Cp, Wh, bh, use_sigmoid, img);
     ONR_LAUNCH_CHECK();
     return 0;
 }
@@ -260,7 +263,8 @@ int onr_head_bwd_dz(const float* gimg, const float* img, const void* dsilu, int 
     const int ppb = threads / chunks;
     size_t grid = (npix + (size_t)ppb * kDzUnroll - 1) / ((size_t)ppb * kDzUnroll);
     if (grid > (size_t)num_sms() * 8) grid = (size_t)num_sms() * 8;
-    head_bwd_dz_kernel<<<(int)grid, threads, 0, (cudaStream_t)stream>>>(
+    auto kern = B == 1 ? head_bwd_dz_kernel<true> : head_bwd_dz_kernel<false>;
+    kern<<<(int)grid, threads, 0, (cudaStream_t)stream>>>(
         gimg, img, reinterpret_cast<const __nv_bfloat16*>(dsilu), (uint32_t)npix, (uint32_t)(H * W), C, Cp, Wh,
         use_sigmoid, reinterpret_cast<__nv_bfloat16*>(dz));
     ONR_LAUNCH_CHECK();
@@ -278,7 +282,8 @@ int onr_head_bwd_gw(const float* gimg, const float* img, const void* y, int B, i
     const int threads = lanes * chunks;
     int grid = (int)((npix + lanes - 1) / lanes);
     if (grid > num_sms() * 4) grid = num_sms() * 4;
-    head_bwd_gw_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+    auto kern = B == 1 ? head_bwd_gw_kernel<true> : head_bwd_gw_kernel<false>;
+    kern<<<grid, threads, 0, (cudaStream_t)stream>>>(
         gimg, img, reinterpret_cast<const __nv_bfloat16*>(y), (uint32_t)npix, (uint32_t)(H * W), C, Cp,
         use_sigmoid, gWh, gbh);
     ONR_LAUNCH_CHECK();

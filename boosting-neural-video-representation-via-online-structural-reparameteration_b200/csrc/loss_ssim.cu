@@ -22,6 +22,8 @@ constexpr int kTS = 32;
 constexpr int kHalo = kWin - 1;
 constexpr int kIn = kTS + kHalo;   // 42
 constexpr int kPitch = kIn + 1;    // 43
+constexpr int kVR = 8;             // output rows per thread in the vertical passes
+constexpr int kHC = 4;             // output columns per thread in the horizontal passes
 
 // The taps travel as a by-value kernel argument (constant bank), so nothing is uploaded at run time and
 // every launch is CUDA-graph capturable.
@@ -76,52 +78,82 @@ ssim_stats_kernel(const Gauss gw, const float* __restrict__ X, const float* __re
         sy[r][c] = in ? yp[(size_t)gy * W + gx] : 0.0f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kTS * kIn; i += 256) {
-        const int r = i / kIn, c = i % kIn;
-        float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    // vertical pass with a register sliding window: a thread owns one column and kVR consecutive output rows, so
+    // each staged value is read once per kVR outputs (tap order per output is unchanged: k ascending)
+    for (int i = threadIdx.x; i < (kTS / kVR) * kIn; i += 256) {
+        const int c = i % kIn, r0 = (i / kIn) * kVR;
+        float acc[kVR][5];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {
-            const float g = gw.g[k], x = sx[r + k][c], y = sy[r + k][c];
-            a0 = fmaf(g, x, a0);
-            a1 = fmaf(g, y, a1);
-            a2 = fmaf(g, x * x, a2);
-            a3 = fmaf(g, y * y, a3);
-            a4 = fmaf(g, x * y, a4);
+        for (int o = 0; o < kVR; ++o)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) acc[o][q] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kVR + kHalo; ++j) {
+            const float x = sx[r0 + j][c], y = sy[r0 + j][c];
+            const float v[5] = {x, y, x * x, y * y, x * y};
+#pragma unroll
+            for (int o = 0; o < kVR; ++o) {
+                const int k = j - o;
+                if (k >= 0 && k < kWin) {
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) acc[o][q] = fmaf(gw.g[k], v[q], acc[o][q]);
+                }
+            }
         }
-        sv[0][r][c] = a0; sv[1][r][c] = a1; sv[2][r][c] = a2; sv[3][r][c] = a3; sv[4][r][c] = a4;
+#pragma unroll
+        for (int o = 0; o < kVR; ++o)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) sv[q][r0 + o][c] = acc[o][q];
     }
     __syncthreads();
     const float C1 = 1e-4f, C2 = 9e-4f;
     float ssim_sum = 0.0f, cs_sum = 0.0f;
-    for (int i = threadIdx.x; i < kTS * kTS; i += 256) {
-        const int r = i / kTS, c = i % kTS;
-        const int oy = oy0 + r, ox = ox0 + c;
-        if (oy >= Hv || ox >= Wv) continue;
-        float m1 = 0, m2 = 0, q = 0, p = 0, rr = 0;
+    // horizontal pass: a thread owns one row and kHC consecutive output columns; a warp covers 4 rows x 8 column
+    // groups (with the 43-float pitch its 32 shared reads fall in 32 distinct banks, and its global stores stay
+    // within four 128-byte row segments)
+    for (int i = threadIdx.x; i < kTS * (kTS / kHC); i += 256) {
+        const int c0 = (i % (kTS / kHC)) * kHC, r = i / (kTS / kHC);
+        float acc[kHC][5];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {
-            const float g = gw.g[k];
-            m1 = fmaf(g, sv[0][r][c + k], m1);
-            m2 = fmaf(g, sv[1][r][c + k], m2);
-            q = fmaf(g, sv[2][r][c + k], q);
-            p = fmaf(g, sv[3][r][c + k], p);
-            rr = fmaf(g, sv[4][r][c + k], rr);
+        for (int o = 0; o < kHC; ++o)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) acc[o][q] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kHC + kHalo; ++j) {
+            float v[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) v[q] = sv[q][r][c0 + j];
+#pragma unroll
+            for (int o = 0; o < kHC; ++o) {
+                const int k = j - o;
+                if (k >= 0 && k < kWin) {
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) acc[o][q] = fmaf(gw.g[k], v[q], acc[o][q]);
+                }
+            }
         }
-        const float m1s = m1 * m1, m2s = m2 * m2, m12 = m1 * m2;
-        const float s1 = q - m1s, s2 = p - m2s, s12 = rr - m12;
-        const float A1 = 2.0f * m12 + C1, A2 = 2.0f * s12 + C2;
-        const float B1 = m1s + m2s + C1, B2 = s1 + s2 + C2;
-        const float cs = A2 / B2;
-        const float S = (A1 / B1) * cs;
-        ssim_sum += S;
-        cs_sum += cs;
-        if (kGrad) {
-            const float inv = 1.0f / (B1 * B2);
-            const size_t o = ((size_t)plane * Hv + oy) * Wv + ox;
-            const size_t mapsz = (size_t)planes * Hv * Wv;
-            coef[o] = (2.0f * m2 * (A2 - A1) - 2.0f * m1 * S * (B2 - B1)) * inv;
-            coef[mapsz + o] = -S / B2;
-            coef[2 * mapsz + o] = 2.0f * A1 * inv;
+        const int oy = oy0 + r;
+#pragma unroll
+        for (int o = 0; o < kHC; ++o) {
+            const int ox = ox0 + c0 + o;
+            if (oy >= Hv || ox >= Wv) continue;
+            const float m1 = acc[o][0], m2 = acc[o][1], q = acc[o][2], p = acc[o][3], rr = acc[o][4];
+            const float m1s = m1 * m1, m2s = m2 * m2, m12 = m1 * m2;
+            const float s1 = q - m1s, s2 = p - m2s, s12 = rr - m12;
+            const float A1 = 2.0f * m12 + C1, A2 = 2.0f * s12 + C2;
+            const float B1 = m1s + m2s + C1, B2 = s1 + s2 + C2;
+            const float cs = A2 / B2;
+            const float S = (A1 / B1) * cs;
+            ssim_sum += S;
+            cs_sum += cs;
+            if (kGrad) {
+                const float inv = 1.0f / (B1 * B2);
+                const size_t oo = ((size_t)plane * Hv + oy) * Wv + ox;
+                const size_t mapsz = (size_t)planes * Hv * Wv;
+                coef[oo] = (2.0f * m2 * (A2 - A1) - 2.0f * m1 * S * (B2 - B1)) * inv;
+                coef[mapsz + oo] = -S / B2;
+                coef[2 * mapsz + oo] = 2.0f * A1 * inv;
+            }
         }
     }
     const float t0 = block_sum(ssim_sum, sred);
@@ -153,40 +185,63 @@ fusion_bwd_kernel(const Gauss gw, const float* __restrict__ X, const float* __re
         for (int qn = 0; qn < 3; ++qn) sc[qn][r][c] = in ? coef[qn * mapsz + o] : 0.0f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kTS * kIn; i += 256) {
-        const int r = i / kIn, c = i % kIn;
-        float a0 = 0, a1 = 0, a2 = 0;
+    // transposed ("full") filter, same sliding-window layout as the statistics kernel; the window is walked
+    // downwards so that each output still accumulates its taps in ascending k
+    for (int i = threadIdx.x; i < (kTS / kVR) * kIn; i += 256) {
+        const int c = i % kIn, r0 = (i / kIn) * kVR;
+        float acc[kVR][3];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {
-            const float g = gw.g[k];
-            a0 = fmaf(g, sc[0][r + kHalo - k][c], a0);
-            a1 = fmaf(g, sc[1][r + kHalo - k][c], a1);
-            a2 = fmaf(g, sc[2][r + kHalo - k][c], a2);
+        for (int o = 0; o < kVR; ++o) acc[o][0] = acc[o][1] = acc[o][2] = 0.0f;
+#pragma unroll
+        for (int j = kVR + kHalo - 1; j >= 0; --j) {
+            const float v[3] = {sc[0][r0 + j][c], sc[1][r0 + j][c], sc[2][r0 + j][c]};
+#pragma unroll
+            for (int o = 0; o < kVR; ++o) {
+                const int k = o + kHalo - j;
+                if (k >= 0 && k < kWin) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) acc[o][q] = fmaf(gw.g[k], v[q], acc[o][q]);
+                }
+            }
         }
-        sv[0][r][c] = a0; sv[1][r][c] = a1; sv[2][r][c] = a2;
+#pragma unroll
+        for (int o = 0; o < kVR; ++o) {
+            sv[0][r0 + o][c] = acc[o][0]; sv[1][r0 + o][c] = acc[o][1]; sv[2][r0 + o][c] = acc[o][2];
+        }
     }
     __syncthreads();
     float l1 = 0.0f, l2 = 0.0f;
-    for (int i = threadIdx.x; i < kTS * kTS; i += 256) {
-        const int r = i / kTS, c = i % kTS;
-        const int y = y0 + r, x = x0 + c;
-        if (y >= H || x >= W) continue;
-        float tm = 0, tq = 0, tr = 0;
+    for (int i = threadIdx.x; i < kTS * (kTS / kHC); i += 256) {
+        const int c0 = (i % (kTS / kHC)) * kHC, r = i / (kTS / kHC);
+        float acc[kHC][3];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {
-            const float g = gw.g[k];
-            tm = fmaf(g, sv[0][r][c + kHalo - k], tm);
-            tq = fmaf(g, sv[1][r][c + kHalo - k], tq);
-            tr = fmaf(g, sv[2][r][c + kHalo - k], tr);
+        for (int o = 0; o < kHC; ++o) acc[o][0] = acc[o][1] = acc[o][2] = 0.0f;
+#pragma unroll
+        for (int j = kHC + kHalo - 1; j >= 0; --j) {
+            const float v[3] = {sv[0][r][c0 + j], sv[1][r][c0 + j], sv[2][r][c0 + j]};
+#pragma unroll
+            for (int o = 0; o < kHC; ++o) {
+                const int k = o + kHalo - j;
+                if (k >= 0 && k < kWin) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) acc[o][q] = fmaf(gw.g[k], v[q], acc[o][q]);
+                }
+            }
         }
-        const size_t idx = ((size_t)plane * H + y) * W + x;
-        const float xv = X[idx], yv = Y[idx];
-        const float d = xv - yv;
-        l1 += fabsf(d);
-        l2 = fmaf(d, d, l2);
-        if (grad) {
-            const float sgn = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f);
-            grad[idx] = k_l1 * sgn + k_ssim * (tm + 2.0f * xv * tq + yv * tr);
+        const int y = y0 + r;
+#pragma unroll
+        for (int o = 0; o < kHC; ++o) {
+            const int x = x0 + c0 + o;
+            if (y >= H || x >= W) continue;
+            const size_t idx = ((size_t)plane * H + y) * W + x;
+            const float xv = X[idx], yv = Y[idx];
+            const float d = xv - yv;
+            l1 += fabsf(d);
+            l2 = fmaf(d, d, l2);
+            if (grad) {
+                const float sgn = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f);
+                grad[idx] = k_l1 * sgn + k_ssim * (acc[o][0] + 2.0f * xv * acc[o][1] + yv * acc[o][2]);
+            }
         }
     }
     const float t0 = block_sum(l1, sred);

@@ -14,6 +14,8 @@ model.py:611-625 / :518-567.  PyTorch only provides the allocations and the stre
 import ctypes as C
 import math
 
+import os
+
 import torch
 
 from . import _lib
@@ -126,7 +128,16 @@ class NetExecutor:
         # ---- per block weights / gradient staging ------------------------------------------------
         self.K, self.bias, self.T, self.wf, self.wd, self.bias_p = [], [], [], [], [], []
         self.dKp, self.dbias_p, self.dK, self.dbias, self.dT = [], [], [], [], []
-        for g, blk in zip(self.geoms, gen.layers):
+        # the wgrad kernels accumulate (red.global.add) into dKp / dbias_p: all of them live in one pool that a
+        # single memset clears per step
+        pool_off, total = [], 0
+        for g in self.geoms:
+            a = total
+            b = a + -(-(g.nk * 9 * g.cpi) // 64) * 64
+            total = b + -(-g.nk // 64) * 64
+            pool_off.append((a, b))
+        self._wgrad_pool = zeros(total) if train else None
+        for (g, blk), (off_k, off_b) in zip(zip(self.geoms, gen.layers), pool_off):
             erb = blk.is_erb_train()
             self.K.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
             self.bias.append(zeros(g.cout) if erb else None)
@@ -135,8 +146,8 @@ class NetExecutor:
             self.wd.append(zeros(9, g.cpi_rows, g.nk, dtype=bf16) if train else None)
             self.bias_p.append(zeros(g.npad))
             if train:
-                self.dKp.append(zeros(g.nk, 9, g.cpi))
-                self.dbias_p.append(zeros(g.nk))
+                self.dKp.append(self._wgrad_pool[off_k:off_k + g.nk * 9 * g.cpi].view(g.nk, 9, g.cpi))
+                self.dbias_p.append(self._wgrad_pool[off_b:off_b + g.nk])
                 self.dK.append(zeros(g.cout, g.cin, 3, 3))
                 self.dbias.append(zeros(g.cout))
                 self.dT.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
@@ -165,7 +176,7 @@ class NetExecutor:
                     lib, B=B, H=g.h, W=g.w, x=ptr(self.x[l]), x_cp=g.cpi,
                     dz=ptr(self.dz[l + 1]), dz_cp=g.cpo, s=g.s,
                     dKp=ptr(self.dKp[l]), dbias_p=ptr(self.dbias_p[l])))
-        self._zero_list = [t for t in self.dKp + self.dbias_p if t is not None]
+        self._wgrad_on_side = os.environ.get("ONR_WGRAD_SIDE", "1") != "0"
 
     # ------------------------------------------------------------------------------------- helpers
     def _block_kernel(self, l):
@@ -274,8 +285,6 @@ class NetExecutor:
         single-branch conv gradients)."""
         assert self.train
         gen, st, lib = self.gen, _lib.stream(), self.lib
-        for t in self._zero_list:
-            t.zero_()
         head = gen.head_conv()
         hname = gen.head_name()
         gL = self.geoms[-1]
@@ -288,6 +297,9 @@ class NetExecutor:
         hside = self._side_streams()[0]
         hside.wait_event(fork)
         with torch.cuda.stream(hside):
+            self._wgrad_pool.zero_()
+            pool_clear = torch.cuda.Event()
+            pool_clear.record(hside)
             check(lib.onr_head_bwd_gw(
                 ptr(gimg), ptr(self.img), ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
                 1 if gen.sigmoid else 0, ptr(grads[hname + ".weight"]), ptr(grads[hname + ".bias"]), _lib.stream()),
@@ -298,16 +310,23 @@ class NetExecutor:
         check(lib.onr_head_bwd_dz(
             ptr(gimg), ptr(self.img), ptr(self.d[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
             ptr(head.weight), 1 if gen.sigmoid else 0, ptr(self.dz[self.L]), st), "onr_head_bwd_dz")
+        if not self._wgrad_on_side:
+            main.wait_event(pool_clear)
         for l in reversed(range(self.L)):
             g, blk = self.geoms[l], gen.layers[l]
-            check(lib.onr_wgrad_plan_run(self.wgrad[l].handle, st), "onr_wgrad_plan_run")
-            # un-pack + fold backward of block l run on a side stream, overlapped with the remaining dgrads
+            # dz[l+1] is ready: wgrad -> un-pack -> fold backward of block l run on a side stream beside the
+            # dgrad chain (only the dgrads and the stem backward are on the critical path)
+            if not self._wgrad_on_side:
+                check(lib.onr_wgrad_plan_run(self.wgrad[l].handle, st), "onr_wgrad_plan_run")
             done = torch.cuda.Event()
             done.record(main)
             side = self._side_streams()[l]
             side.wait_event(done)
             with torch.cuda.stream(side):
                 sst = _lib.stream()
+                if self._wgrad_on_side:
+                    side.wait_event(pool_clear)
+                    check(lib.onr_wgrad_plan_run(self.wgrad[l].handle, sst), "onr_wgrad_plan_run")
                 if blk.is_erb_train():
                     dK, db = self.dK[l], self.dbias[l]
                 else:   # single-branch block: dK is the parameter gradient itself (grads are zero on entry)

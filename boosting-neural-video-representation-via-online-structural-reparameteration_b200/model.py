@@ -289,14 +289,16 @@ class Generator(nn.Module):
         return ex
 
     def alloc_grads(self):
-        """Zeroed fp32 gradient tensors, one per parameter, carved from a single flat buffer."""
+        """Zeroed fp32 gradient tensors, one per parameter, carved from a single flat buffer (each slice starts
+        on a 256-byte boundary so the optimizer and the kernels can use 128-bit accesses)."""
         named = list(self.named_parameters())
-        total = sum(p.numel() for _, p in named)
+        align = 64
+        total = sum(-(-p.numel() // align) * align for _, p in named)
         flat = torch.zeros(total, dtype=torch.float32, device=named[0][1].device)
         grads, off = {}, 0
         for n, p in named:
             grads[n] = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            off += -(-p.numel() // align) * align
         grads["__flat__"] = flat
         return grads
 

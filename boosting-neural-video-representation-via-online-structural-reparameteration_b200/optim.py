@@ -61,8 +61,14 @@ class FusedAdam(torch.optim.Optimizer):
         cached = self._tables.get(gi)
         if cached is None or cached[0] != key:
             dev = params[0].device
-            table = torch.tensor(rows, dtype=torch.int64).to(dev)
-            cached = (key, table, max(r[4] for r in rows), len(rows), dev)
+            lib = _lib.lib()
+            per_block, per_call = int(lib.onr_adam_block_elems()), int(lib.onr_adam_max_tensors())
+            calls = []
+            for i in range(0, len(rows), per_call):
+                part = rows[i:i + per_call]
+                table = torch.tensor(part, dtype=torch.int64).to(dev)
+                calls.append((table, sum(-(-r[4] // per_block) for r in part), len(part)))
+            cached = (key, calls, dev)
             self._tables[gi] = cached
         return cached
 
@@ -71,6 +77,7 @@ class FusedAdam(torch.optim.Optimizer):
         if getattr(self, "_lr_dev", None) is None or self._lr_dev.device != dev:
             self._lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
             self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._hyp_dev = torch.zeros(2, dtype=torch.float32, device=dev)   # kernel scratch (bias corrections)
         return self._lr_dev, self._step_dev
 
     def _upload(self, lr, step, dev):
@@ -99,12 +106,14 @@ class FusedAdam(torch.optim.Optimizer):
             cached = self._table(gi, group)
             if cached is None:
                 continue
-            _, table, max_numel, n, dev = cached
+            _, calls, dev = cached
             if not device_schedule:
                 self._upload(float(group['lr']), self._step_count_host, dev)
             lr_dev, step_dev = self.device_scalars(dev)
             b1, b2 = group['betas']
-            check(lib.onr_adam_multi(ptr(table), n, max_numel, ptr(lr_dev), ptr(step_dev), b1, b2, group['eps'],
-                                     float(self.grad_scale), 1 if self.fused_zero_grad else 0, _lib.stream()),
-                  "onr_adam_multi")
+            for table, total_blocks, n in calls:
+                check(lib.onr_adam_multi(ptr(table), n, total_blocks, ptr(lr_dev), ptr(step_dev),
+                                         ptr(self._hyp_dev), b1, b2,
+                                         group['eps'], float(self.grad_scale), 1 if self.fused_zero_grad else 0,
+                                         _lib.stream()), "onr_adam_multi")
         return loss

@@ -190,10 +190,15 @@ int onr_msssim(const float* pred, const float* target, int B, int H, int W, floa
  * torch.optim.Adam as used at main_train.py:196, :248-250 (betas (beta,0.999), eps 1e-8, no wd).
  * table: n_tensors entries {param, grad, m, v, numel} as 5 x uint64 each (device array).
  * lr_dev, step_dev: device scalars (lr from adjust_lr, utils.py:240-259; step count t >= 1).
- * grad_scale multiplies grads (1/world_size); grads are zeroed after use when zero_grad != 0. */
-int onr_adam_multi(const uint64_t* table, int n_tensors, size_t max_numel /* largest tensor */,
-                   const float* lr_dev, const int* step_dev, float beta1, float beta2, float eps,
-                   float grad_scale, int zero_grad, void* stream);
+ * grad_scale multiplies grads (1/world_size); grads are zeroed after use when zero_grad != 0.
+ * One CTA updates one onr_adam_block_elems()-element piece of one tensor: total_blocks is the sum over the
+ * table of ceil(numel / onr_adam_block_elems()); at most onr_adam_max_tensors() entries per call.
+ * hyp_scratch: 2 floats of device memory the call overwrites (bias corrections, evaluated once in double). */
+size_t onr_adam_block_elems(void);
+int onr_adam_max_tensors(void);
+int onr_adam_multi(const uint64_t* table, int n_tensors, size_t total_blocks,
+                   const float* lr_dev, const int* step_dev, float* hyp_scratch, float beta1, float beta2,
+                   float eps, float grad_scale, int zero_grad, void* stream);
 
 /* adjust_lr (utils.py:240-259) on the device: step_dev += 1, lr_dev = lr0 * multiplier(step) with
  * cur_epoch = epoch + iter/data_size.  lr_type 0 = cosine, 1 = const; warm-up 0.1 -> 1 over `warmup` epochs. */
