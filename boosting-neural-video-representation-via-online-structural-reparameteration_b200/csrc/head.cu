@@ -225,6 +225,82 @@ head_bwd_gw_kernel(const float* __restrict__ gimg, const float* __restrict__ img
     if (threadIdx.x < 3) atomicAdd(&gbh[threadIdx.x], sg[3 * Cp + threadIdx.x]);
 }
 
+// Both halves in one pass over the pixels (same thread layout): reads y and SiLU'(z), writes dz, reduces gWh / gbh.
+// Less total work than the two separate kernels (g_pre and the loop overhead are shared), but the reduction then
+// sits on the critical path; onr_head_bwd uses it, the split entry points remain for callers that overlap them.
+constexpr int kFusedUnroll = 2;
+template <bool kOne>
+__global__ void __launch_bounds__(384)
+head_bwd_fused_kernel(const float* __restrict__ gimg, const float* __restrict__ img,
+                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dsilu, uint32_t npix,
+                      uint32_t HW, int C, int Cp, const float* __restrict__ Wh, int use_sigmoid,
+                      float* __restrict__ gWh, float* __restrict__ gbh, __nv_bfloat16* __restrict__ dz) {
+    __shared__ float sg[3 * kHeadMaxC + 3];
+    for (int i = threadIdx.x; i < 3 * Cp + 3; i += blockDim.x) sg[i] = 0.0f;
+    __syncthreads();
+    const int chunks = Cp / 8;
+    const int lanes = blockDim.x / chunks;
+    const int lane = threadIdx.x / chunks, ch = threadIdx.x - lane * chunks;
+    float w[3][8], gw[3][8];
+    head_load_w(Wh, C, ch, w);
+    float gb[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gw[k][e] = 0.0f;
+    const uint32_t stride = gridDim.x * lanes;
+    for (uint32_t pix0 = blockIdx.x * lanes + lane; pix0 < npix; pix0 += kFusedUnroll * stride) {
+        uint4 yv[kFusedUnroll], dv[kFusedUnroll];
+        float gp[kFusedUnroll][3];
+#pragma unroll
+        for (int u = 0; u < kFusedUnroll; ++u) {
+            const bool ok = pix0 + u * stride < npix;
+            const uint32_t pix = ok ? pix0 + u * stride : pix0;
+            yv[u] = __ldg(reinterpret_cast<const uint4*>(y) + pix * chunks + ch);
+            dv[u] = __ldg(reinterpret_cast<const uint4*>(dsilu) + pix * chunks + ch);
+            head_gpre<kOne>(gimg, img, pix, HW, use_sigmoid, gp[u]);
+            if (!ok) gp[u][0] = gp[u][1] = gp[u][2] = 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < kFusedUnroll; ++u) {
+            const uint32_t pix = pix0 + u * stride;
+            const uint32_t yu[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+            const uint32_t du[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+            uint32_t out[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float y0 = bf16_lo(yu[e]), y1 = bf16_hi(yu[e]);
+                float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    gw[k][e * 2] = fmaf(gp[u][k], y0, gw[k][e * 2]);
+                    gw[k][e * 2 + 1] = fmaf(gp[u][k], y1, gw[k][e * 2 + 1]);
+                    d0 = fmaf(gp[u][k], w[k][2 * e], d0);
+                    d1 = fmaf(gp[u][k], w[k][2 * e + 1], d1);
+                }
+                out[e] = pack_bf16x2(d0 * bf16_lo(du[e]), d1 * bf16_hi(du[e]));
+            }
+            gb[0] += gp[u][0];
+            gb[1] += gp[u][1];
+            gb[2] += gp[u][2];
+            if (pix < npix)
+                reinterpret_cast<uint4*>(dz)[pix * chunks + ch] = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&sg[k * Cp + ch * 8 + e], gw[k][e]);
+        if (ch == 0) atomicAdd(&sg[3 * Cp + k], gb[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * Cp; i += blockDim.x) {
+        const int k = i / Cp, c = i % Cp;
+        if (c < C) atomicAdd(&gWh[k * C + c], sg[i]);
+    }
+    if (threadIdx.x < 3) atomicAdd(&gbh[threadIdx.x], sg[3 * Cp + threadIdx.x]);
+}
+
 // threads per block: a multiple of `chunks` close to `target`, holding whole pixels
 static inline int head_threads(int chunks, int target) { return (target / chunks) * chunks; }
 static inline bool head_fits_u32(size_t npix, int chunks) { return npix * (size_t)chunks * 3 < (1ull << 31); }
@@ -293,9 +369,21 @@ int onr_head_bwd_gw(const float* gimg, const float* img, const void* y, int B, i
 int onr_head_bwd(const float* gimg, const float* img, const void* y, const void* dsilu, int B, int H, int W,
                  int C, int Cp, const float* Wh, int use_sigmoid, float* gWh, float* gbh, void* dz,
                  void* stream) {
-    int rc = onr_head_bwd_dz(gimg, img, dsilu, B, H, W, C, Cp, Wh, use_sigmoid, dz, stream);
-    if (rc) return rc;
-    return onr_head_bwd_gw(gimg, img, y, B, H, W, C, Cp, use_sigmoid, gWh, gbh, stream);
+    using namespace onr;
+    ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
+    const size_t npix = (size_t)B * H * W;
+    const int chunks = Cp / 8;
+    ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
+    const int lanes = 384 / chunks;
+    const int threads = lanes * chunks;
+    int grid = (int)((npix + lanes - 1) / lanes);
+    if (grid > num_sms() * 4) grid = num_sms() * 4;
+    auto kern = B == 1 ? head_bwd_fused_kernel<true> : head_bwd_fused_kernel<false>;
+    kern<<<grid, threads, 0, (cudaStream_t)stream>>>(
+        gimg, img, reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dsilu),
+        (uint32_t)npix, (uint32_t)(H * W), C, Cp, Wh, use_sigmoid, gWh, gbh, reinterpret_cast<__nv_bfloat16*>(dz));
+    ONR_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // extern "C"

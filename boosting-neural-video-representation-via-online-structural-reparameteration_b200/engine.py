@@ -177,6 +177,7 @@ class NetExecutor:
                     dz=ptr(self.dz[l + 1]), dz_cp=g.cpo, s=g.s,
                     dKp=ptr(self.dKp[l]), dbias_p=ptr(self.dbias_p[l])))
         self._wgrad_on_side = os.environ.get("ONR_WGRAD_SIDE", "1") != "0"
+        self._head_fused = os.environ.get("ONR_HEAD_FUSED", "1") != "0"
 
     # ------------------------------------------------------------------------------------- helpers
     def _block_kernel(self, l):
@@ -290,8 +291,6 @@ class NetExecutor:
         gL = self.geoms[-1]
         main = torch.cuda.current_stream()
         joins = []
-        # head backward: the weight/bias gradient reduction runs on a side stream (nothing downstream needs it
-        # before Adam); only dz = (Wh^T g_pre) * SiLU' stays on the critical path
         fork = torch.cuda.Event()
         fork.record(main)
         hside = self._side_streams()[0]
@@ -300,16 +299,25 @@ class NetExecutor:
             self._wgrad_pool.zero_()
             pool_clear = torch.cuda.Event()
             pool_clear.record(hside)
-            check(lib.onr_head_bwd_gw(
-                ptr(gimg), ptr(self.img), ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
-                1 if gen.sigmoid else 0, ptr(grads[hname + ".weight"]), ptr(grads[hname + ".bias"]), _lib.stream()),
-                "onr_head_bwd_gw")
-            ev = torch.cuda.Event()
-            ev.record(hside)
-            joins.append(ev)
-        check(lib.onr_head_bwd_dz(
-            ptr(gimg), ptr(self.img), ptr(self.d[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
-            ptr(head.weight), 1 if gen.sigmoid else 0, ptr(self.dz[self.L]), st), "onr_head_bwd_dz")
+        if self._head_fused:
+            # one pass over the pixels: dz = (Wh^T g_pre) * SiLU' and the head weight/bias gradient reduction
+            check(lib.onr_head_bwd(
+                ptr(gimg), ptr(self.img), ptr(self.x[self.L]), ptr(self.d[self.L]), self.B, self.H, self.W,
+                self.C_last, gL.cpo, ptr(head.weight), 1 if gen.sigmoid else 0, ptr(grads[hname + ".weight"]),
+                ptr(grads[hname + ".bias"]), ptr(self.dz[self.L]), st), "onr_head_bwd")
+        else:
+            # split: the reduction on a side stream, only dz on the critical path
+            with torch.cuda.stream(hside):
+                check(lib.onr_head_bwd_gw(
+                    ptr(gimg), ptr(self.img), ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
+                    1 if gen.sigmoid else 0, ptr(grads[hname + ".weight"]), ptr(grads[hname + ".bias"]),
+                    _lib.stream()), "onr_head_bwd_gw")
+                ev = torch.cuda.Event()
+                ev.record(hside)
+                joins.append(ev)
+            check(lib.onr_head_bwd_dz(
+                ptr(gimg), ptr(self.img), ptr(self.d[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
+                ptr(head.weight), 1 if gen.sigmoid else 0, ptr(self.dz[self.L]), st), "onr_head_bwd_dz")
         if not self._wgrad_on_side:
             main.wait_event(pool_clear)
         for l in reversed(range(self.L)):
