@@ -83,7 +83,7 @@ _SIGNATURES = {
     "onr_loss_workspace_bytes": (sz, [i32, i32, i32]),
     "onr_fusion6_fwd_bwd": (i32, [vp, vp, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp]),
     "onr_msssim_workspace_bytes": (sz, [i32, i32, i32]),
-    "onr_msssim": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+    "onr_msssim": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "onr_adam_block_elems": (sz, []),
     "onr_adam_max_tensors": (i32, []),
     "onr_adam_multi": (i32, [vp, i32, sz, vp, vp, vp, f32, f32, f32, f32, i32, vp]),

@@ -268,9 +268,13 @@ __global__ void fusion_finalize_kernel(const double* __restrict__ gacc, const do
     out5[4] = (float)(-10.0 * log10(mse));
 }
 
-// avg_pool2d(kernel 2, stride 2, padding (ph, pw), count_include_pad)
-__global__ void avgpool2_kernel(const float* __restrict__ in, int planes, int H, int W, int ph, int pw, int Ho,
-                                int Wo, float* __restrict__ out) {
+// avg_pool2d(kernel 2, stride 2, padding (ph, pw), count_include_pad) of both images of a scale in one launch
+// (blockIdx.y selects prediction / target)
+__global__ void avgpool2_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int planes, int H,
+                                int W, int ph, int pw, int Ho, int Wo, float* __restrict__ out0,
+                                float* __restrict__ out1) {
+    const float* __restrict__ in = blockIdx.y ? in1 : in0;
+    float* __restrict__ out = blockIdx.y ? out1 : out0;
     const size_t total = (size_t)planes * Ho * Wo;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
@@ -292,7 +296,8 @@ __global__ void avgpool2_kernel(const float* __restrict__ in, int planes, int H,
 
 struct MsDims { int H[5], W[5]; };
 
-__global__ void msssim_finalize_kernel(const double* __restrict__ acc /* [5][planes][2] */, int planes,
+__global__ void msssim_finalize_kernel(const double* __restrict__ acc /* [5][planes][2] */,
+                                       const double* __restrict__ acc0 /* scale 0: [planes][2] */, int planes,
                                        MsDims dims, float* __restrict__ out1) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double wts[5] = {0.0448, 0.2856, 0.3001, 0.2363, 0.1333};
@@ -301,7 +306,7 @@ __global__ void msssim_finalize_kernel(const double* __restrict__ acc /* [5][pla
         double prod = 1.0;
         for (int l = 0; l < 5; ++l) {
             const double nv = (double)(dims.H[l] - kHalo) * (double)(dims.W[l] - kHalo);
-            const double* a = acc + ((size_t)l * planes + p) * 2;
+            const double* a = l == 0 ? acc0 + (size_t)p * 2 : acc + ((size_t)l * planes + p) * 2;
             double v = (l < 4 ? a[1] : a[0]) / nv;
             // the reference does this in fp32: relu then pow
             float vf = (float)v;
@@ -379,7 +384,7 @@ size_t onr_msssim_workspace_bytes(int B, int H, int W) {
 }
 
 int onr_msssim(const float* pred, const float* target, int B, int H, int W, float* out1, void* work,
-               void* stream) {
+               const void* loss_work, void* stream) {
     using namespace onr;
     MsDims d;
     ms_dims(H, W, &d);
@@ -394,11 +399,19 @@ int onr_msssim(const float* pred, const float* target, int B, int H, int W, floa
     uint8_t* cur = wp + acc_bytes;
     const float* x = pred;
     const float* y = target;
+    // scale 0 is the plain SSIM of the loss: when the caller hands over the workspace of an onr_fusion6_fwd_bwd
+    // call on the same images (already ordered before this one), its per-plane sums are reused
+    const double* acc0 = loss_work ? reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(loss_work) +
+                                                                     align256(16 * sizeof(double)))
+                                   : acc;
     for (int l = 0; l < 5; ++l) {
         const int Hl = d.H[l], Wl = d.W[l];
-        dim3 g(ceil_div(Wl - kHalo, kTS), ceil_div(Hl - kHalo, kTS), planes);
-        ssim_stats_kernel<false><<<g, 256, 0, st>>>(gw, x, y, Hl, Wl, acc + (size_t)l * planes * 2, nullptr, planes);
-        ONR_LAUNCH_CHECK();
+        if (l > 0 || !loss_work) {
+            dim3 g(ceil_div(Wl - kHalo, kTS), ceil_div(Hl - kHalo, kTS), planes);
+            ssim_stats_kernel<false><<<g, 256, 0, st>>>(gw, x, y, Hl, Wl, acc + (size_t)l * planes * 2, nullptr,
+                                                        planes);
+            ONR_LAUNCH_CHECK();
+        }
         if (l < 4) {
             const int Ho = d.H[l + 1], Wo = d.W[l + 1];
             const size_t nb = align256((size_t)planes * Ho * Wo * sizeof(float));
@@ -408,15 +421,13 @@ int onr_msssim(const float* pred, const float* target, int B, int H, int W, floa
             const size_t total = (size_t)planes * Ho * Wo;
             int grid = (int)((total + 255) / 256);
             if (grid > num_sms() * 16) grid = num_sms() * 16;
-            avgpool2_kernel<<<grid, 256, 0, st>>>(x, planes, Hl, Wl, Hl % 2, Wl % 2, Ho, Wo, nx);
-            ONR_LAUNCH_CHECK();
-            avgpool2_kernel<<<grid, 256, 0, st>>>(y, planes, Hl, Wl, Hl % 2, Wl % 2, Ho, Wo, ny);
+            avgpool2_kernel<<<dim3(grid, 2), 256, 0, st>>>(x, y, planes, Hl, Wl, Hl % 2, Wl % 2, Ho, Wo, nx, ny);
             ONR_LAUNCH_CHECK();
             x = nx;
             y = ny;
         }
     }
-    msssim_finalize_kernel<<<1, 32, 0, st>>>(acc, planes, d, out1);
+    msssim_finalize_kernel<<<1, 32, 0, st>>>(acc, acc0, planes, d, out1);
     ONR_LAUNCH_CHECK();
     return 0;
 }

@@ -76,10 +76,12 @@ class FrameFitter:
         B, H, W = self.B, self.H, self.W
         check(lib.onr_frame_u8_to_f32(ptr(self.frame_u8), self.frame_u8.numel(), ptr(self.target), st), "u8_to_f32")
         img = self.ex.forward(t_norm=self.t_norm, freqs=self.freqs)
+        check(lib.onr_fusion6_fwd_bwd(ptr(img), ptr(self.target), B, H, W, self.w_l1, self.w_ssim, 1.0,
+                                      ptr(self.out), ptr(self.gimg), ptr(self.loss_work), st), "onr_fusion6_fwd_bwd")
         ms_done = None
         if self.with_msssim:
-            # the MS-SSIM metric (reference main_train.py:254) only needs the image: run it on a side stream,
-            # concurrently with the loss and the whole backward
+            # the MS-SSIM metric (reference main_train.py:254) runs on a side stream, concurrently with the whole
+            # backward; its first scale is the SSIM the loss has just evaluated, so it starts after the loss
             main = torch.cuda.current_stream()
             if getattr(self, "_ms_stream", None) is None:
                 self._ms_stream = torch.cuda.Stream(device=self.dev)
@@ -88,11 +90,9 @@ class FrameFitter:
             self._ms_stream.wait_event(fork)
             with torch.cuda.stream(self._ms_stream):
                 check(lib.onr_msssim(ptr(img), ptr(self.target), B, H, W, ptr(self.out[5:6]), ptr(self.ms_work),
-                                     _lib.stream()), "onr_msssim")
+                                     ptr(self.loss_work), _lib.stream()), "onr_msssim")
                 ms_done = torch.cuda.Event()
                 ms_done.record(self._ms_stream)
-        check(lib.onr_fusion6_fwd_bwd(ptr(img), ptr(self.target), B, H, W, self.w_l1, self.w_ssim, 1.0,
-                                      ptr(self.out), ptr(self.gimg), ptr(self.loss_work), st), "onr_fusion6_fwd_bwd")
         self.ex.backward(self.gimg, self.grads)
         if ms_done is not None:
             torch.cuda.current_stream().wait_event(ms_done)

@@ -136,7 +136,7 @@ def msssim_fn(output_list, target_list):
             B, _, H, W = p.shape
             out1 = torch.empty(1, dtype=torch.float32, device=p.device)
             work = _workspace("msssim", lib.onr_msssim_workspace_bytes(B, H, W), p.device)
-            check(lib.onr_msssim(ptr(p), ptr(t), B, H, W, ptr(out1), ptr(work), _lib.stream()), "onr_msssim")
+            check(lib.onr_msssim(ptr(p), ptr(t), B, H, W, ptr(out1), ptr(work), None, _lib.stream()), "onr_msssim")
             vals.append(out1.view(1))
         else:
             vals.append(torch.zeros(1, device=output.device))

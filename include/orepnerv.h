@@ -184,7 +184,9 @@ int onr_fusion6_fwd_bwd(const float* pred, const float* target, int B, int H, in
 /* utils.py:201-211 / pytorch_msssim.ms_ssim: 5 scales, avg_pool2d(2, padding = dim%2). out[1]. */
 size_t onr_msssim_workspace_bytes(int B, int H, int W);
 int onr_msssim(const float* pred, const float* target, int B, int H, int W, float* out1,
-               void* work, void* stream);
+               void* work, const void* loss_work /* NULL, or the workspace of an onr_fusion6_fwd_bwd call on
+               the same (pred, target) ordered before this call: its scale-0 statistics are reused */,
+               void* stream);
 
 /* ------------------------------------------------------------------ A9: fused multi-tensor Adam
  * torch.optim.Adam as used at main_train.py:196, :248-250 (betas (beta,0.999), eps 1e-8, no wd).

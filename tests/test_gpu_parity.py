@@ -254,6 +254,22 @@ def test_metrics_against_golden(dev, golden):
     assert abs(msssim_fn([x.to(dev)], [y.to(dev)]).item() - O.ms_ssim(x, y).item()) <= 2e-5
     small = torch.rand(1, 3, 64, 64)
     assert msssim_fn([small.to(dev)], [small.to(dev)]).item() == 0.0      # H < 160 -> 0 (utils.py:204-207)
+    # the training step hands MS-SSIM the loss workspace so that scale 0 (= the SSIM of the loss) is not filtered
+    # twice: same value as the standalone evaluation
+    from orepnerv import _lib
+    from orepnerv._lib import check, ptr
+    lib = _lib.lib()
+    xd, yd = x.to(dev).contiguous(), y.to(dev).contiguous()
+    B, _, H, W = xd.shape
+    lw = torch.zeros(lib.onr_loss_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+    mw = torch.zeros(lib.onr_msssim_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+    out, ms = torch.zeros(8, device=dev), torch.zeros(2, device=dev)
+    check(lib.onr_fusion6_fwd_bwd(ptr(xd), ptr(yd), B, H, W, 0.7, 0.3, 1.0, ptr(out), None, ptr(lw), _lib.stream()),
+          "fusion6")
+    check(lib.onr_msssim(ptr(xd), ptr(yd), B, H, W, ptr(ms[0:1]), ptr(mw), ptr(lw), _lib.stream()), "msssim")
+    check(lib.onr_msssim(ptr(xd), ptr(yd), B, H, W, ptr(ms[1:2]), ptr(mw), None, _lib.stream()), "msssim")
+    assert abs(ms[0].item() - ms[1].item()) <= 1e-6
+    assert abs(ms[0].item() - O.ms_ssim(x, y).item()) <= 2e-5
 
 
 def test_adam_matches_oracle(dev):
