@@ -4,6 +4,7 @@
 // Thread layout: 8-channel (16-byte) chunks, (Cp/8) consecutive threads per pixel, so a warp touches one
 // contiguous span of the activation.
 #include "onr_common.cuh"
+#include "onr_ptx.cuh"
 
 namespace onr {
 
@@ -301,6 +302,130 @@ head_bwd_fused_kernel(const float* __restrict__ gimg, const float* __restrict__ 
     if (threadIdx.x < 3) atomicAdd(&gbh[threadIdx.x], sg[3 * Cp + threadIdx.x]);
 }
 
+// The same fused backward fed by the bulk-copy engine (single image, H*W % 4 == 0): one persistent CTA per SM, a
+// producer warp streams 128-pixel tiles of y, SiLU'(z) and the six gimg / img plane segments into a ring of shared
+// memory stages (cp.async.bulk + mbarrier transaction counts), 32 * chunks consumer threads reduce them.  The whole
+// ring is in flight while a tile is being consumed, which a register-fed loop at this register count cannot do.
+constexpr int kHbPix = 128;          // pixels per stage
+constexpr int kHbMaxStages = 4;
+struct HeadStream {
+    const float* gimg; const float* img; const __nv_bfloat16* y; const __nv_bfloat16* dsilu;
+    uint32_t npix; int C, Cp; const float* Wh; int use_sigmoid;
+    float* gWh; float* gbh; __nv_bfloat16* dz; int stages;
+};
+__global__ void __launch_bounds__(544, 1) head_bwd_stream_kernel(const HeadStream a) {
+    extern __shared__ __align__(128) uint8_t hs_smem[];
+    __shared__ float sg[3 * kHeadMaxC + 3];
+    __shared__ __align__(8) uint64_t bars[2 * kHbMaxStages];
+    const int chunks = a.Cp / 8;
+    const uint32_t act_bytes = kHbPix * a.Cp * 2, stage_bytes = 2 * act_bytes + 6 * kHbPix * 4;
+    const int S = a.stages;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kHbMaxStages]);
+    const int n_cons_warps = chunks;           // 32 * chunks consumer threads
+    for (int i = threadIdx.x; i < 3 * a.Cp + 3; i += blockDim.x) sg[i] = 0.0f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, n_cons_warps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const uint32_t ntiles = (a.npix + kHbPix - 1) / kHbPix;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        // ---------------------------------------------------------------- producer
+        if (elect_one()) {
+            uint32_t it = 0;
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int s = it % S;
+                if (it >= (uint32_t)S) mbar_wait(empty0 + 8 * s, ((it / S) - 1) & 1);
+                const uint32_t pix0 = t * kHbPix;
+                const uint32_t np = min((uint32_t)kHbPix, a.npix - pix0);
+                const uint32_t dst = smem_u32(hs_smem) + s * stage_bytes;
+                const uint32_t bar = full0 + 8 * s;
+                mbar_expect_tx(bar, 2 * np * a.Cp * 2 + 6 * np * 4);
+                bulk_load_1d(dst, a.y + (size_t)pix0 * a.Cp, np * a.Cp * 2, bar);
+                bulk_load_1d(dst + act_bytes, a.dsilu + (size_t)pix0 * a.Cp, np * a.Cp * 2, bar);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    bulk_load_1d(dst + 2 * act_bytes + k * kHbPix * 4, a.gimg + (size_t)k * a.npix + pix0, np * 4,
+                                 bar);
+                    bulk_load_1d(dst + 2 * act_bytes + (3 + k) * kHbPix * 4, a.img + (size_t)k * a.npix + pix0,
+                                 np * 4, bar);
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- consumers
+        const int ct = threadIdx.x - 32;
+        const int lane_px = ct / chunks, ch = ct - lane_px * chunks;   // 32 pixel lanes x chunks
+        float w[3][8], gw[3][8];
+        head_load_w(a.Wh, a.C, ch, w);
+        float gb[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) gw[k][e] = 0.0f;
+        uint32_t it = 0;
+        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int s = it % S;
+            mbar_wait(full0 + 8 * s, (it / S) & 1);
+            const uint8_t* st = hs_smem + (size_t)s * stage_bytes;
+            const uint4* sy = reinterpret_cast<const uint4*>(st);
+            const uint4* sd = reinterpret_cast<const uint4*>(st + act_bytes);
+            const float* sgi = reinterpret_cast<const float*>(st + 2 * act_bytes);
+            const uint32_t pix0 = t * kHbPix;
+            const uint32_t np = min((uint32_t)kHbPix, a.npix - pix0);
+#pragma unroll
+            for (int j = 0; j < kHbPix / 32; ++j) {
+                const uint32_t p = j * 32 + lane_px;
+                if (p >= np) continue;
+                const uint4 yv = sy[p * chunks + ch], dv = sd[p * chunks + ch];
+                float gp[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float g = sgi[k * kHbPix + p], o = sgi[(3 + k) * kHbPix + p];
+                    gp[k] = a.use_sigmoid ? g * o * (1.0f - o) : g * 2.0f * o * (1.0f - o);
+                }
+                const uint32_t yu[4] = {yv.x, yv.y, yv.z, yv.w};
+                const uint32_t du[4] = {dv.x, dv.y, dv.z, dv.w};
+                uint32_t out[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float y0 = bf16_lo(yu[e]), y1 = bf16_hi(yu[e]);
+                    float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        gw[k][e * 2] = fmaf(gp[k], y0, gw[k][e * 2]);
+                        gw[k][e * 2 + 1] = fmaf(gp[k], y1, gw[k][e * 2 + 1]);
+                        d0 = fmaf(gp[k], w[k][2 * e], d0);
+                        d1 = fmaf(gp[k], w[k][2 * e + 1], d1);
+                    }
+                    out[e] = pack_bf16x2(d0 * bf16_lo(du[e]), d1 * bf16_hi(du[e]));
+                }
+                gb[0] += gp[0]; gb[1] += gp[1]; gb[2] += gp[2];
+                reinterpret_cast<uint4*>(a.dz)[(size_t)(pix0 + p) * chunks + ch] =
+                    make_uint4(out[0], out[1], out[2], out[3]);
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(empty0 + 8 * s);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&sg[k * a.Cp + ch * 8 + e], gw[k][e]);
+            if (ch == 0) atomicAdd(&sg[3 * a.Cp + k], gb[k]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * a.Cp; i += blockDim.x) {
+        const int k = i / a.Cp, c = i % a.Cp;
+        if (c < a.C) atomicAdd(&a.gWh[k * a.C + c], sg[i]);
+    }
+    if (threadIdx.x < 3) atomicAdd(&a.gbh[threadIdx.x], sg[3 * a.Cp + threadIdx.x]);
+}
+
 // threads per block: a multiple of `chunks` close to `target`, holding whole pixels
 static inline int head_threads(int chunks, int target) { return (target / chunks) * chunks; }
 static inline bool head_fits_u32(size_t npix, int chunks) { return npix * (size_t)chunks * 3 < (1ull << 31); }
@@ -374,6 +499,27 @@ int onr_head_bwd(const float* gimg, const float* img, const void* y, const void*
     const size_t npix = (size_t)B * H * W;
     const int chunks = Cp / 8;
     ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
+    static const bool no_stream = getenv("ONR_HEAD_STREAM") && atoi(getenv("ONR_HEAD_STREAM")) == 0;
+    if (B == 1 && npix % 4 == 0 && !no_stream) {
+        const size_t stage_bytes = 2 * (size_t)kHbPix * Cp * 2 + 6 * kHbPix * 4;
+        int stages = (int)((200 * 1024) / stage_bytes);
+        if (stages > kHbMaxStages) stages = kHbMaxStages;
+        ONR_REQUIRE(stages >= 2, "head: stage does not fit shared memory");
+        static bool attr_set = false;
+        if (!attr_set) {
+            ONR_CUDA(cudaFuncSetAttribute(head_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+            attr_set = true;
+        }
+        HeadStream hs{gimg, img, reinterpret_cast<const __nv_bfloat16*>(y),
+                      reinterpret_cast<const __nv_bfloat16*>(dsilu), (uint32_t)npix, C, Cp, Wh, use_sigmoid,
+                      gWh, gbh, reinterpret_cast<__nv_bfloat16*>(dz), stages};
+        const int ntiles = (int)((npix + kHbPix - 1) / kHbPix);
+        const int grid = ntiles < num_sms() ? ntiles : num_sms();
+        head_bwd_stream_kernel<<<grid, 32 + 32 * chunks, stages * stage_bytes, (cudaStream_t)stream>>>(hs);
+        ONR_LAUNCH_CHECK();
+        return 0;
+    }
     const int lanes = 384 / chunks;
     const int threads = lanes * chunks;
     int grid = (int)((npix + lanes - 1) / lanes);

@@ -92,6 +92,13 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src,
         "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+// 1-D bulk copy global -> shared (no tensor map): dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
