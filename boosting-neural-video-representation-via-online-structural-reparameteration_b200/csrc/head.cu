@@ -426,6 +426,94 @@ __global__ void __launch_bounds__(544, 1) head_bwd_stream_kernel(const HeadStrea
     if (threadIdx.x < 3) atomicAdd(&a.gbh[threadIdx.x], sg[3 * a.Cp + threadIdx.x]);
 }
 
+// Forward in the same streaming form: the ring holds 128-pixel tiles of y.  Four lanes share a pixel, lane q
+// owning the 16-byte chunks q, q+4, ... (CPT of them) with their weights in registers; two xor-shuffles finish the
+// three dot products inside the warp, so consumer warps never meet at a barrier and run decoupled from each other.
+struct HeadFwdStream {
+    const __nv_bfloat16* y; uint32_t npix; int C, Cp; const float* Wh; const float* bh; int use_sigmoid;
+    float* img; int stages;
+};
+constexpr int kHfConsumers = 256;   // 8 warps x 8 pixels per pass
+template <int CPT>
+__global__ void __launch_bounds__(32 + kHfConsumers, 1) head_fwd_stream_kernel(const HeadFwdStream a) {
+    extern __shared__ __align__(128) uint8_t hs_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * 8];
+    constexpr int chunks = 4 * CPT;
+    const uint32_t stage_bytes = kHbPix * chunks * 16;
+    const int S = a.stages;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, kHfConsumers / 32);   // one arrival per consumer warp
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const uint32_t ntiles = (a.npix + kHbPix - 1) / kHbPix;
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            uint32_t it = 0;
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int s = it % S;
+                if (it >= (uint32_t)S) mbar_wait(empty0 + 8 * s, ((it / S) - 1) & 1);
+                const uint32_t pix0 = t * kHbPix;
+                const uint32_t np = min((uint32_t)kHbPix, a.npix - pix0);
+                const uint32_t bar = full0 + 8 * s;
+                mbar_expect_tx(bar, np * chunks * 16);
+                bulk_load_1d(smem_u32(hs_smem) + s * stage_bytes, a.y + (size_t)pix0 * a.Cp, np * chunks * 16, bar);
+            }
+        }
+        return;
+    }
+    const int ct = threadIdx.x - 32;
+    const int q = ct & 3, pl = ct >> 2;           // lane within the pixel, pixel within the pass (0..63)
+    float w[CPT][3][8];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) head_load_w(a.Wh, a.C, q + 4 * i, w[i]);
+    const float bias = q < 3 ? __ldg(a.bh + q) : 0.0f;
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % S;
+        mbar_wait(full0 + 8 * s, (it / S) & 1);
+        const uint4* sy = reinterpret_cast<const uint4*>(hs_smem + (size_t)s * stage_bytes);
+        const uint32_t pix0 = t * kHbPix;
+        const uint32_t np = min((uint32_t)kHbPix, a.npix - pix0);
+        float res[kHbPix * 4 / kHfConsumers];
+#pragma unroll
+        for (int j = 0; j < kHbPix * 4 / kHfConsumers; ++j) {
+            const uint32_t p = j * (kHfConsumers / 4) + pl;
+            const uint32_t pc = p < np ? p : 0;       // lanes beyond a partial tile re-read pixel 0 (not stored)
+            float acc[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                const uint4 v = sy[pc * chunks + q + 4 * i];
+                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float lo = bf16_lo(u[e]), hi = bf16_hi(u[e]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        acc[k] = fmaf(hi, w[i][k][2 * e + 1], fmaf(lo, w[i][k][2 * e], acc[k]));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+                acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+            }
+            res[j] = q == 0 ? acc[0] : (q == 1 ? acc[1] : acc[2]);
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty0 + 8 * s);   // the stage has been read
+#pragma unroll
+        for (int j = 0; j < kHbPix * 4 / kHfConsumers; ++j) {
+            const uint32_t p = j * (kHfConsumers / 4) + pl;
+            if (q < 3 && p < np) a.img[(size_t)q * a.npix + pix0 + p] = head_act(res[j] + bias, a.use_sigmoid);
+        }
+    }
+}
+
 // threads per block: a multiple of `chunks` close to `target`, holding whole pixels
 static inline int head_threads(int chunks, int target) { return (target / chunks) * chunks; }
 static inline bool head_fits_u32(size_t npix, int chunks) { return npix * (size_t)chunks * 3 < (1ull << 31); }
@@ -441,6 +529,26 @@ int onr_head_fwd(const void* y, int B, int H, int W, int C, int Cp, const float*
     const size_t npix = (size_t)B * H * W;
     const int chunks = Cp / 8;
     ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
+    static const bool no_stream = getenv("ONR_HEAD_STREAM") && atoi(getenv("ONR_HEAD_STREAM")) == 0;
+    if (B == 1 && !no_stream) {
+        const size_t stage_bytes = (size_t)kHbPix * Cp * 2;
+        int stages = (int)((160 * 1024) / stage_bytes);
+        if (stages > 8) stages = 8;
+        auto kern = chunks == 4 ? head_fwd_stream_kernel<1> : chunks == 8 ? head_fwd_stream_kernel<2>
+                  : chunks == 12 ? head_fwd_stream_kernel<3> : head_fwd_stream_kernel<4>;
+        static bool attr_set[4] = {false, false, false, false};
+        if (!attr_set[chunks / 4 - 1]) {
+            ONR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[chunks / 4 - 1] = true;
+        }
+        HeadFwdStream hs{reinterpret_cast<const __nv_bfloat16*>(y), (uint32_t)npix, C, Cp, Wh, bh, use_sigmoid, img,
+                         stages};
+        const int ntiles = (int)((npix + kHbPix - 1) / kHbPix);
+        const int grid = ntiles < num_sms() ? ntiles : num_sms();
+        kern<<<grid, 32 + kHfConsumers, stages * stage_bytes, (cudaStream_t)stream>>>(hs);
+        ONR_LAUNCH_CHECK();
+        return 0;
+    }
     const int threads = head_threads(chunks, 384);
     const int ppb = threads / chunks;
     ONR_REQUIRE(3 * ppb <= threads, "head: block too small to finish its pixels");
