@@ -48,7 +48,7 @@ struct GemmArgs {
 // contractions (tens to a few hundred tiles, K from 52 to 5850), so the tile is small to fill the machine without
 // a cross-CTA split (the forward fold must be deterministic) and the CTA's 8 warps split every K slab four ways:
 // k-group kg = tid/64 multiplies k in [kg*GK/4, (kg+1)*GK/4) of the slab with a 4x4 register block per thread
-// (two 16-byte shared loads per 16 FMAs); the four partial tiles are summed in a fixed order at the end.
+// (two 16-byte shared loads per 8 packed FFMA2 = 16 FMAs); the four partial tiles are summed in a fixed order at the end.
 // AKF / BKF: the operand is staged with k running fastest across a warp (8 k x 4 rows per warp: whole 32-byte
 // sectors of a k-contiguous operand, conflict-free shared stores) or with the m / n index fastest.
 constexpr int GT = 32;        // tile edge
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) fold_gemm_kernel(const GemmArgs g) {
     };
 
     const int kg = tid >> 6, t = tid & 63, tx = t & 7, ty = t >> 3;
-    float acc[4][4] = {};
+    uint64_t acc2[4][2] = {};   // 4x4 register block as fp32 pairs (columns 0-1, 2-3): 8 FFMA2 per k
     fetch(k_begin);
     for (int k0 = k_begin; k0 < k_end; k0 += GK) {
 #pragma unroll
@@ -125,13 +125,21 @@ __global__ void __launch_bounds__(256) fold_gemm_kernel(const GemmArgs g) {
             const int k = kg * KPG + kk;
             const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
             const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const uint64_t b01 = pack2(b.x, b.y), b23 = pack2(b.z, b.w);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int i = 0; i < 4; ++i) {
+                fma2_s(acc2[i][0], av[i], b01);
+                fma2_s(acc2[i][1], av[i], b23);
+            }
         }
         __syncthreads();
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc[i][0] = lo2(acc2[i][0]); acc[i][1] = hi2(acc2[i][0]);
+        acc[i][2] = lo2(acc2[i][1]); acc[i][3] = hi2(acc2[i][1]);
     }
     // fixed-order sum of the four k-group partials
     if (kg > 0) {

@@ -82,28 +82,32 @@ ssim_stats_kernel(const Gauss gw, const float* __restrict__ X, const float* __re
     // each staged value is read once per kVR outputs (tap order per output is unchanged: k ascending)
     for (int i = threadIdx.x; i < (kTS / kVR) * kIn; i += 256) {
         const int c = i % kIn, r0 = (i / kIn) * kVR;
-        float acc[kVR][5];
+        // the five filtered quantities travel as two fp32 pairs (x,y), (xx,yy) + xy: 2 FFMA2 + 1 FFMA per tap
+        uint64_t a01[kVR], a23[kVR];
+        float a4[kVR];
 #pragma unroll
-        for (int o = 0; o < kVR; ++o)
-#pragma unroll
-            for (int q = 0; q < 5; ++q) acc[o][q] = 0.0f;
+        for (int o = 0; o < kVR; ++o) { a01[o] = 0ull; a23[o] = 0ull; a4[o] = 0.0f; }
 #pragma unroll
         for (int j = 0; j < kVR + kHalo; ++j) {
             const float x = sx[r0 + j][c], y = sy[r0 + j][c];
-            const float v[5] = {x, y, x * x, y * y, x * y};
+            const uint64_t v01 = pack2(x, y), v23 = pack2(x * x, y * y);
+            const float v4 = x * y;
 #pragma unroll
             for (int o = 0; o < kVR; ++o) {
                 const int k = j - o;
                 if (k >= 0 && k < kWin) {
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) acc[o][q] = fmaf(gw.g[k], v[q], acc[o][q]);
+                    fma2_s(a01[o], gw.g[k], v01);
+                    fma2_s(a23[o], gw.g[k], v23);
+                    a4[o] = fmaf(gw.g[k], v4, a4[o]);
                 }
             }
         }
 #pragma unroll
-        for (int o = 0; o < kVR; ++o)
-#pragma unroll
-            for (int q = 0; q < 5; ++q) sv[q][r0 + o][c] = acc[o][q];
+        for (int o = 0; o < kVR; ++o) {
+            sv[0][r0 + o][c] = lo2(a01[o]); sv[1][r0 + o][c] = hi2(a01[o]);
+            sv[2][r0 + o][c] = lo2(a23[o]); sv[3][r0 + o][c] = hi2(a23[o]);
+            sv[4][r0 + o][c] = a4[o];
+        }
     }
     __syncthreads();
     const float C1 = 1e-4f, C2 = 9e-4f;
@@ -113,24 +117,31 @@ ssim_stats_kernel(const Gauss gw, const float* __restrict__ X, const float* __re
     // within four 128-byte row segments)
     for (int i = threadIdx.x; i < kTS * (kTS / kHC); i += 256) {
         const int c0 = (i % (kTS / kHC)) * kHC, r = i / (kTS / kHC);
-        float acc[kHC][5];
+        uint64_t a01[kHC], a23[kHC];
+        float a4[kHC];
 #pragma unroll
-        for (int o = 0; o < kHC; ++o)
-#pragma unroll
-            for (int q = 0; q < 5; ++q) acc[o][q] = 0.0f;
+        for (int o = 0; o < kHC; ++o) { a01[o] = 0ull; a23[o] = 0ull; a4[o] = 0.0f; }
 #pragma unroll
         for (int j = 0; j < kHC + kHalo; ++j) {
-            float v[5];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) v[q] = sv[q][r][c0 + j];
+            const uint64_t v01 = pack2(sv[0][r][c0 + j], sv[1][r][c0 + j]);
+            const uint64_t v23 = pack2(sv[2][r][c0 + j], sv[3][r][c0 + j]);
+            const float v4 = sv[4][r][c0 + j];
 #pragma unroll
             for (int o = 0; o < kHC; ++o) {
                 const int k = j - o;
                 if (k >= 0 && k < kWin) {
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) acc[o][q] = fmaf(gw.g[k], v[q], acc[o][q]);
+                    fma2_s(a01[o], gw.g[k], v01);
+                    fma2_s(a23[o], gw.g[k], v23);
+                    a4[o] = fmaf(gw.g[k], v4, a4[o]);
                 }
             }
+        }
+        float acc[kHC][5];
+#pragma unroll
+        for (int o = 0; o < kHC; ++o) {
+            acc[o][0] = lo2(a01[o]); acc[o][1] = hi2(a01[o]);
+            acc[o][2] = lo2(a23[o]); acc[o][3] = hi2(a23[o]);
+            acc[o][4] = a4[o];
         }
         const int oy = oy0 + r;
 #pragma unroll
@@ -189,45 +200,52 @@ fusion_bwd_kernel(const Gauss gw, const float* __restrict__ X, const float* __re
     // downwards so that each output still accumulates its taps in ascending k
     for (int i = threadIdx.x; i < (kTS / kVR) * kIn; i += 256) {
         const int c = i % kIn, r0 = (i / kIn) * kVR;
-        float acc[kVR][3];
+        uint64_t a01[kVR];
+        float a2[kVR];
 #pragma unroll
-        for (int o = 0; o < kVR; ++o) acc[o][0] = acc[o][1] = acc[o][2] = 0.0f;
+        for (int o = 0; o < kVR; ++o) { a01[o] = 0ull; a2[o] = 0.0f; }
 #pragma unroll
         for (int j = kVR + kHalo - 1; j >= 0; --j) {
-            const float v[3] = {sc[0][r0 + j][c], sc[1][r0 + j][c], sc[2][r0 + j][c]};
+            const uint64_t v01 = pack2(sc[0][r0 + j][c], sc[1][r0 + j][c]);
+            const float v2 = sc[2][r0 + j][c];
 #pragma unroll
             for (int o = 0; o < kVR; ++o) {
                 const int k = o + kHalo - j;
                 if (k >= 0 && k < kWin) {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) acc[o][q] = fmaf(gw.g[k], v[q], acc[o][q]);
+                    fma2_s(a01[o], gw.g[k], v01);
+                    a2[o] = fmaf(gw.g[k], v2, a2[o]);
                 }
             }
         }
 #pragma unroll
         for (int o = 0; o < kVR; ++o) {
-            sv[0][r0 + o][c] = acc[o][0]; sv[1][r0 + o][c] = acc[o][1]; sv[2][r0 + o][c] = acc[o][2];
+            sv[0][r0 + o][c] = lo2(a01[o]); sv[1][r0 + o][c] = hi2(a01[o]); sv[2][r0 + o][c] = a2[o];
         }
     }
     __syncthreads();
     float l1 = 0.0f, l2 = 0.0f;
     for (int i = threadIdx.x; i < kTS * (kTS / kHC); i += 256) {
         const int c0 = (i % (kTS / kHC)) * kHC, r = i / (kTS / kHC);
-        float acc[kHC][3];
+        uint64_t a01[kHC];
+        float a2[kHC];
 #pragma unroll
-        for (int o = 0; o < kHC; ++o) acc[o][0] = acc[o][1] = acc[o][2] = 0.0f;
+        for (int o = 0; o < kHC; ++o) { a01[o] = 0ull; a2[o] = 0.0f; }
 #pragma unroll
         for (int j = kHC + kHalo - 1; j >= 0; --j) {
-            const float v[3] = {sv[0][r][c0 + j], sv[1][r][c0 + j], sv[2][r][c0 + j]};
+            const uint64_t v01 = pack2(sv[0][r][c0 + j], sv[1][r][c0 + j]);
+            const float v2 = sv[2][r][c0 + j];
 #pragma unroll
             for (int o = 0; o < kHC; ++o) {
                 const int k = o + kHalo - j;
                 if (k >= 0 && k < kWin) {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) acc[o][q] = fmaf(gw.g[k], v[q], acc[o][q]);
+                    fma2_s(a01[o], gw.g[k], v01);
+                    a2[o] = fmaf(gw.g[k], v2, a2[o]);
                 }
             }
         }
+        float acc[kHC][3];
+#pragma unroll
+        for (int o = 0; o < kHC; ++o) { acc[o][0] = lo2(a01[o]); acc[o][1] = hi2(a01[o]); acc[o][2] = a2[o]; }
         const int y = y0 + r;
 #pragma unroll
         for (int o = 0; o < kHC; ++o) {

@@ -79,6 +79,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// Packed fp32 FMA (sm_100 FFMA2): two IEEE fma.rn per instruction, so results are bit-identical to two scalar
+// FFMAs at half the issue slots.  fma2_s broadcasts a scalar multiplicand (ptxas folds the {a,a} pair into the
+// instruction's scalar-operand form, no extra move).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi2(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ void fma2_s(uint64_t& acc, float a, uint64_t b) {
+    const uint64_t aa = pack2(a, a);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(aa), "l"(b));
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
