@@ -433,7 +433,7 @@ struct HeadFwdStream {
     const __nv_bfloat16* y; uint32_t npix; int C, Cp; const float* Wh; const float* bh; int use_sigmoid;
     float* img; int stages;
 };
-constexpr int kHfConsumers = 256;   // 8 warps x 8 pixels per pass
+constexpr int kHfConsumers = 512;   // 16 warps x 8 pixels: one 128-pixel tile per pass
 template <int CPT>
 __global__ void __launch_bounds__(32 + kHfConsumers, 1) head_fwd_stream_kernel(const HeadFwdStream a) {
     extern __shared__ __align__(128) uint8_t hs_smem[];

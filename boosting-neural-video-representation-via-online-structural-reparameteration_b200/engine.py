@@ -178,6 +178,7 @@ class NetExecutor:
                     dKp=ptr(self.dKp[l]), dbias_p=ptr(self.dbias_p[l])))
         self._wgrad_on_side = os.environ.get("ONR_WGRAD_SIDE", "1") != "0"
         self._head_fused = os.environ.get("ONR_HEAD_FUSED", "1") != "0"
+        self._fold_chain = int(os.environ.get("ONR_FOLD_CHAIN", "0"))
 
     # ------------------------------------------------------------------------------------- helpers
     def _block_kernel(self, l):
@@ -228,9 +229,14 @@ class NetExecutor:
         fork = torch.cuda.Event()
         fork.record(main)
         events = []
+        chain = self._fold_chain if self.train else 0
         for l, g in enumerate(self.geoms):
             side = self._side_streams()[l]
             side.wait_event(fork)
+            if l > 0 and chain == 1:
+                side.wait_event(events[l - 1])      # one fold after the other, block 0 first
+            elif l > 0 and chain == 2:
+                side.wait_event(events[0])          # block 0 (which gates the first convolution) alone, then the rest
             with torch.cuda.stream(side):
                 st = _lib.stream()
                 K, b = self._block_kernel(l)

@@ -487,3 +487,50 @@ def test_host_pipeline_matches_plain_steps(dev, golden):
     assert outs[0].shape == outs[1].shape == (5, 5)
     # training kernels accumulate in a run-dependent order (atomics, concurrent issuers): compare within bf16 noise
     torch.testing.assert_close(outs[0], outs[1], rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(1, 20, 36, 96), (1, 33, 44, 26), (2, 20, 36, 96), (1, 16, 200, 112)])
+def test_head_kernels_vs_torch(dev, B, H, W, C):
+    """RGB head (model.py:601, :620-623) forward / backward kernels against plain PyTorch fp32 on the same bf16
+    activations.  B = 1 takes the bulk-copy streaming kernels (720 and 1452 pixels: ragged last 128-pixel tile),
+    B = 2 the register-fed ones; the fused backward must agree with its split halves."""
+    from orepnerv import _lib
+    from orepnerv._lib import check, ptr
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    Cp = (C + 31) // 32 * 32
+    y = torch.zeros(B, H, W, Cp)
+    y[..., :C] = torch.randn(B, H, W, C, generator=g)
+    dsilu = torch.zeros(B, H, W, Cp)
+    dsilu[..., :C] = torch.rand(B, H, W, C, generator=g) * 1.2 - 0.1
+    y_d, ds_d = y.to(dev).bfloat16().contiguous(), dsilu.to(dev).bfloat16().contiguous()
+    Wh = (torch.randn(3, C, generator=g) * 0.2).to(dev)
+    bh = (torch.randn(3, generator=g) * 0.1).to(dev)
+    gimg = torch.randn(B, 3, H, W, generator=g).to(dev)
+    img = torch.zeros(B, 3, H, W, device=dev)
+    st = _lib.stream()
+    check(lib.onr_head_fwd(ptr(y_d), B, H, W, C, Cp, ptr(Wh), ptr(bh), 0, ptr(img), st), "head_fwd")
+    yf = y_d.float()[..., :C].requires_grad_(True)
+    Wr, br = Wh.clone().requires_grad_(True), bh.clone().requires_grad_(True)
+    ref = (torch.tanh(torch.einsum('bhwc,kc->bkhw', yf, Wr) + br.view(1, 3, 1, 1)) + 1) * 0.5
+    assert (img - ref).abs().max().item() <= 2e-5
+    ref.backward(gimg)
+    dz_ref = yf.grad * ds_d.float()[..., :C]
+
+    def run(fused):
+        gW, gb = torch.zeros(3, C, device=dev), torch.zeros(3, device=dev)
+        dz = torch.zeros(B, H, W, Cp, device=dev, dtype=torch.bfloat16)
+        if fused:
+            check(lib.onr_head_bwd(ptr(gimg), ptr(img), ptr(y_d), ptr(ds_d), B, H, W, C, Cp, ptr(Wh), 0, ptr(gW),
+                                   ptr(gb), ptr(dz), st), "head_bwd")
+        else:
+            check(lib.onr_head_bwd_dz(ptr(gimg), ptr(img), ptr(ds_d), B, H, W, C, Cp, ptr(Wh), 0, ptr(dz), st), "dz")
+            check(lib.onr_head_bwd_gw(ptr(gimg), ptr(img), ptr(y_d), B, H, W, C, Cp, 0, ptr(gW), ptr(gb), st), "gw")
+        return gW, gb, dz.float()
+
+    for fused in (True, False):
+        gW, gb, dz = run(fused)
+        assert rel_l2(gW, Wr.grad) <= 1e-4, fused
+        assert rel_l2(gb, br.grad) <= 1e-4, fused
+        assert rel_l2(dz[..., :C], dz_ref) <= 6e-3, fused          # dz is stored as bf16
+        assert dz[..., C:].abs().max().item() == 0.0 if Cp > C else True
