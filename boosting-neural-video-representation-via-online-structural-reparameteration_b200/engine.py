@@ -217,6 +217,9 @@ class NetExecutor:
                 ts = ([conv.weight_orig, conv.weight_mask] if hasattr(conv, "weight_orig") else [conv.weight])
                 ts.append(conv.bias)
             key += [(t.data_ptr(), t._version) for t in ts]
+        # FrameFitter updates parameters through raw pointers inside a CUDA graph (no per-tensor version bump): it
+        # advances this counter instead
+        key.append(getattr(self.gen, "_weights_epoch", 0))
         return tuple(key)
 
     def refresh_weights(self):
@@ -238,16 +241,20 @@ class NetExecutor:
             elif l > 0 and chain == 2:
                 side.wait_event(events[0])          # block 0 (which gates the first convolution) alone, then the rest
             with torch.cuda.stream(side):
-                st = _lib.stream()
-                K, b = self._block_kernel(l)
-                check(self.lib.onr_pack_weights(
-                    ptr(K), ptr(b), g.cin, g.cnew, g.s, g.npad, g.cpi_rows,
-                    ptr(self.wf[l]), ptr(self.wd[l]) if self.train else None, ptr(self.bias_p[l]), st),
-                    "onr_pack_weights")
+                self.fold_pack_block(l)
                 ev = torch.cuda.Event()
                 ev.record(side)
             events.append(ev)
         return events
+
+    def fold_pack_block(self, l):
+        """Fold (ERB) + pack block l's kernel into the bf16 operand layouts on the current stream."""
+        g, st = self.geoms[l], _lib.stream()
+        K, b = self._block_kernel(l)
+        check(self.lib.onr_pack_weights(
+            ptr(K), ptr(b), g.cin, g.cnew, g.s, g.npad, g.cpi_rows,
+            ptr(self.wf[l]), ptr(self.wd[l]) if self.train else None, ptr(self.bias_p[l]), st),
+            "onr_pack_weights")
 
     # ------------------------------------------------------------------------------------- forward
     def forward(self, embed=None, t_norm=None, freqs=None, refresh=True):
@@ -286,10 +293,14 @@ class NetExecutor:
         return self.img
 
     # ------------------------------------------------------------------------------------ backward
-    def backward(self, gimg, grads):
+    def backward(self, gimg, grads, block_hook=None):
         """Backward of `forward`. `grads` maps parameter name -> fp32 gradient tensor; every tensor must be
         zero on entry (the kernels accumulate into the ERB branch / stem / head gradients and overwrite the
-        single-branch conv gradients)."""
+        single-branch conv gradients).
+
+        block_hook(l), if given, is called on block l's side stream once that block's parameter gradients are
+        complete AND its dgrad has been issued (nothing in this backward reads the block's weights, packed operands
+        or T afterwards): a trainer can update the block and re-fold it for the next step right there."""
         assert self.train
         gen, st, lib = self.gen, _lib.stream(), self.lib
         head = gen.head_conv()
@@ -354,6 +365,15 @@ class NetExecutor:
                 ev.record(side)
                 joins.append(ev)
             check(lib.onr_conv_plan_run(self.dgrad[l].handle, st), "onr_conv_plan_run(dgrad)")
+            if block_hook is not None:
+                issued = torch.cuda.Event()
+                issued.record(main)
+                side.wait_event(issued)
+                with torch.cuda.stream(side):
+                    block_hook(l)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    joins.append(ev)
         lin1 = gen.stem[0]
         lin2 = gen.stem[2]
         g0 = self.geoms[0]

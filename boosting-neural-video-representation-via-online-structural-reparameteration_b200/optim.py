@@ -46,10 +46,12 @@ class FusedAdam(torch.optim.Optimizer):
         self._tables = {}
 
     # ---- table of raw pointers -------------------------------------------------------------------
-    def _table(self, gi, group):
-        params = [p for p in group['params'] if p.grad is not None]
+    def _table(self, gi, group, subset=None):
+        params = [p for p in (group['params'] if subset is None else subset) if p.grad is not None]
         if not params:
             return None
+        if subset is not None:
+            gi = (gi, tuple(id(p) for p in subset))
         rows = []
         for p in params:
             if p.grad.dtype != torch.float32 or p.dtype != torch.float32 or not p.is_cuda:
@@ -96,6 +98,26 @@ class FusedAdam(torch.optim.Optimizer):
         step_dev.copy_(self._ring[1][i:i + 1], non_blocking=True)
 
     @torch.no_grad()
+    def step_params(self, params):
+        """Adam update of a subset of the (single) parameter group, reading the learning rate and step count the
+        caller has already advanced on the device (onr_sched_tick).  Lets a trainer update a block's parameters as
+        soon as its gradients exist; the host step count is the caller's to advance once per optimisation step."""
+        if len(self.param_groups) != 1:
+            raise RuntimeError("step_params needs a single parameter group")
+        lib, group = _lib.lib(), self.param_groups[0]
+        cached = self._table(0, group, subset=list(params))
+        if cached is None:
+            return
+        _, calls, dev = cached
+        lr_dev, step_dev = self.device_scalars(dev)
+        b1, b2 = group['betas']
+        for table, total_blocks, n in calls:
+            check(lib.onr_adam_multi(ptr(table), n, total_blocks, ptr(lr_dev), ptr(step_dev),
+                                     ptr(self._hyp_dev), b1, b2,
+                                     group['eps'], float(self.grad_scale), 1 if self.fused_zero_grad else 0,
+                                     _lib.stream()), "onr_adam_multi")
+
+    @torch.no_grad()
     def step(self, closure=None, device_schedule=False):
         """One Adam update.  With device_schedule=True the caller has already advanced the device-side
         step counter / learning rate (onr_sched_tick), e.g. inside a captured CUDA graph."""
@@ -116,4 +138,8 @@ class FusedAdam(torch.optim.Optimizer):
                                          ptr(self._hyp_dev), b1, b2,
                                          group['eps'], float(self.grad_scale), 1 if self.fused_zero_grad else 0,
                                          _lib.stream()), "onr_adam_multi")
+            if not torch.cuda.is_current_stream_capturing():
+                # the kernel writes through raw pointers: tell autograd / the decode-side operand cache
+                for p in group['params']:
+                    torch.autograd.graph.increment_version(p)
         return loss

@@ -9,6 +9,8 @@ CUDA graph.  With world_size > 1 every rank fits its own frame (frame-sharded da
 flat fp32 gradient buffer is all-reduced over NCCL before the fused Adam step, which matches the
 reference run with `-b world_size` because every loss term is a batch mean.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -58,6 +60,18 @@ class FrameFitter:
         self.ms_work = (torch.empty(self.lib.onr_msssim_workspace_bytes(self.B, H, W), dtype=torch.uint8, device=dev)
                         if self.with_msssim else None)
         self.freqs = pe.freqs(dev)
+        # Fold-ahead (ONR_FOLD_AHEAD=1; single GPU, device-side LR schedule): a block's parameters are updated on its
+        # side stream as soon as its gradients exist and the block is re-folded / re-packed for the NEXT step right
+        # there, beside the tail of the backward, instead of at the head of the next step where the first
+        # convolutions wait for it.  Same results; measured SLOWER on B200 (759 vs 777 frames/s: the step is bound by
+        # total work, and six Adam launches replace one), hence off by default.
+        self.fold_ahead = (world_size == 1 and args.lr_type in ('cosine', 'const')
+                           and os.environ.get("ONR_FOLD_AHEAD", "0") == "1")
+        named = list(model.named_parameters())
+        self._block_params = [[p for n, p in named if n.startswith(f"layers.{l}.")] for l in range(self.ex.L)]
+        in_blocks = {id(p) for ps in self._block_params for p in ps}
+        self._rest_params = [p for _, p in named if id(p) not in in_blocks]
+        self._weights_valid = False
         self.graph = None
         self.use_graph = use_graph and self.device_sched
         self.host_step = 0
@@ -74,8 +88,10 @@ class FrameFitter:
         """frame conversion, forward, loss + its gradient, backward -> local gradients in self.flat_grad"""
         lib, st = self.lib, _lib.stream()
         B, H, W = self.B, self.H, self.W
+        if self.fold_ahead:
+            self._tick()        # the per-block Adam updates inside the backward need this step's lr / step count
         check(lib.onr_frame_u8_to_f32(ptr(self.frame_u8), self.frame_u8.numel(), ptr(self.target), st), "u8_to_f32")
-        img = self.ex.forward(t_norm=self.t_norm, freqs=self.freqs)
+        img = self.ex.forward(t_norm=self.t_norm, freqs=self.freqs, refresh=not self.fold_ahead)
         check(lib.onr_fusion6_fwd_bwd(ptr(img), ptr(self.target), B, H, W, self.w_l1, self.w_ssim, 1.0,
                                       ptr(self.out), ptr(self.gimg), ptr(self.loss_work), st), "onr_fusion6_fwd_bwd")
         ms_done = None
@@ -93,22 +109,40 @@ class FrameFitter:
                                      ptr(self.loss_work), _lib.stream()), "onr_msssim")
                 ms_done = torch.cuda.Event()
                 ms_done.record(self._ms_stream)
-        self.ex.backward(self.gimg, self.grads)
+        self.ex.backward(self.gimg, self.grads, block_hook=self._update_block if self.fold_ahead else None)
         if ms_done is not None:
             torch.cuda.current_stream().wait_event(ms_done)
 
-    def _body_post(self):
-        """LR schedule tick, fused Adam (+ gradient averaging and zeroing), MS-SSIM metric"""
-        lib, st = self.lib, _lib.stream()
-        B, H, W = self.B, self.H, self.W
-        img = self.ex.img
+    def _update_block(self, l):
+        """backward hook (runs on block l's side stream): Adam on the block's tensors, then fold + pack for the next step"""
+        self.opt.step_params(self._block_params[l])
+        self.ex.fold_pack_block(l)
+
+    def _tick(self):
         lr_dev, step_dev = self.opt.device_scalars(self.dev)
+        a = self.args
+        check(self.lib.onr_sched_tick(ptr(step_dev), ptr(lr_dev), float(a.lr), self.steps_per_epoch, self.data_size,
+                                      int(a.warmup), int(a.epochs), 0 if a.lr_type == 'cosine' else 1, _lib.stream()),
+              "onr_sched_tick")
+
+    def _body_post(self):
+        """LR schedule tick + fused Adam (+ gradient averaging and zeroing); with fold-ahead only the tensors outside
+        the blocks (stem, head) are left to update here"""
+        if self.fold_ahead:
+            self.opt.step_params(self._rest_params)
+            self.opt._step_count_host += 1
+            return
         if self.device_sched:
-            a = self.args
-            check(lib.onr_sched_tick(ptr(step_dev), ptr(lr_dev), float(a.lr), self.steps_per_epoch, self.data_size,
-                                     int(a.warmup), int(a.epochs), 0 if a.lr_type == 'cosine' else 1, st),
-                  "onr_sched_tick")
+            self._tick()
         self.opt.step(device_schedule=self.device_sched)
+
+    def refresh_weights(self):
+        """(Re)folds and packs every block from the current parameters.  Needed before the first step and after
+        anything outside `step` changed the parameters (checkpoint load, roll-back) when fold-ahead is on."""
+        main = torch.cuda.current_stream()
+        for ev in self.ex.refresh_weights():
+            main.wait_event(ev)
+        self._weights_valid = True
 
     def _host_lr(self):
         t = self.host_step
@@ -130,6 +164,8 @@ class FrameFitter:
         if frame_u8 is not None:
             self.load_inputs(frame_u8, t_norm)
         lr = self._host_lr()
+        if self.fold_ahead and not self._weights_valid:
+            self.refresh_weights()
         if self.use_graph:
             if self.graph is None:
                 self._capture()
@@ -143,6 +179,8 @@ class FrameFitter:
         else:
             self._body()
         self.host_step += 1
+        # parameters changed through raw pointers: invalidate operand caches keyed on tensor versions
+        self.model._weights_epoch = getattr(self.model, "_weights_epoch", 0) + 1
         return self.out
 
     def _capture(self):
@@ -169,6 +207,8 @@ class FrameFitter:
             _, step_dev = self.opt.device_scalars(self.dev)
             step_dev.fill_(self.host_step)
         self.opt._step_count_host = self.host_step
+        if self.fold_ahead:
+            self.refresh_weights()       # the packed operands must match the rolled-back parameters
         g = torch.cuda.CUDAGraph()
         if self.world == 1:
             with torch.cuda.graph(g):
@@ -254,3 +294,4 @@ class FrameFitter:
         _, step_dev = self.opt.device_scalars(self.dev)
         step_dev.fill_(self.host_step)
         self.opt._step_count_host = self.host_step
+        self._weights_valid = False          # parameters may have been replaced: re-fold before the next step

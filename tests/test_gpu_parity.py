@@ -534,3 +534,47 @@ def test_head_kernels_vs_torch(dev, B, H, W, C):
         assert rel_l2(gb, br.grad) <= 1e-4, fused
         assert rel_l2(dz[..., :C], dz_ref) <= 6e-3, fused          # dz is stored as bf16
         assert dz[..., C:].abs().max().item() == 0.0 if Cp > C else True
+
+
+def test_fold_ahead_matches_default(dev, golden, monkeypatch):
+    """ONR_FOLD_AHEAD=1 (per-block Adam + next-step fold inside the backward) is a pure re-scheduling: same metrics
+    and parameters as the default order after a few steps."""
+    from orepnerv.trainer import FrameFitter
+    g = golden("small_erb.pt")
+    frames_u8 = (g['target'] * 255).round().to(torch.uint8)
+    args = argparse.Namespace(loss_type='Fusion6', lr=5e-4, lr_type='cosine', warmup=1, epochs=5, beta=0.5,
+                              batchSize=2)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ONR_FOLD_AHEAD", mode)
+        pe, gen = build(g['cfg'], "ERB", dev)
+        fit = FrameFitter(gen, pe, args, data_size=4, steps_per_epoch=2, use_graph=True, with_msssim=False)
+        assert fit.fold_ahead == (mode == "1")
+        outs = [fit.step(frames_u8.to(dev), g['pos'].to(dev))[:5].cpu().clone() for _ in range(4)]
+        res[mode] = (torch.stack(outs), {k: v.detach().cpu().clone() for k, v in gen.state_dict().items()})
+    torch.testing.assert_close(res["0"][0], res["1"][0], rtol=2e-3, atol=2e-4)
+    for k in res["0"][1]:
+        assert rel_l2(res["1"][1][k], res["0"][1][k]) <= 2e-3, k
+
+
+def test_decode_sees_parameters_updated_by_the_fitter(dev, golden):
+    """The fitter updates parameters through raw pointers inside a CUDA graph; the decode-side packed-operand cache
+    must notice (reference main_train.py evaluates the same model object between training epochs)."""
+    import copy
+    from orepnerv.trainer import FrameFitter
+    g = golden("small_erb.pt")
+    frames_u8 = (g['target'] * 255).round().to(torch.uint8)
+    args = argparse.Namespace(loss_type='Fusion6', lr=5e-3, lr_type='cosine', warmup=0, epochs=5, beta=0.5,
+                              batchSize=2)
+    pe, gen = build(g['cfg'], "ERB", dev)
+    embed = pe(g['pos'])
+    with torch.no_grad():
+        before = gen(embed)[0].clone()
+    fit = FrameFitter(gen, pe, args, data_size=4, steps_per_epoch=2, use_graph=True, with_msssim=False)
+    for _ in range(3):
+        fit.step(frames_u8.to(dev), g['pos'].to(dev))
+    with torch.no_grad():
+        after = gen(embed)[0].clone()
+        fresh = copy.deepcopy(gen)(embed)[0]          # new executor, packs from the current parameters
+    assert not torch.equal(after, before)
+    assert torch.equal(after, fresh)
