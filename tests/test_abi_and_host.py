@@ -121,3 +121,26 @@ def test_shard_indices_cover_every_frame():
         seen = [i for p in per_rank for i in p]
         assert set(seen) == set(range(n)) and len(seen) == steps * k
     assert sharding.shard_indices(10, 2, 0, 0, shuffle=False) == [0, 2, 4, 6, 8]
+
+
+def test_flat_gradient_buffer_is_aligned_and_complete(golden):
+    """alloc_grads: one flat fp32 buffer (the all-reduce payload), one view per parameter, every view starting on a
+    256-byte boundary (the fused Adam kernel takes its 128-bit path only on 16-byte aligned tensors), no overlap."""
+    g = golden("tiny_erb.pt")
+    _, gen = build(g, "ERB")
+    grads = gen.alloc_grads()
+    flat = grads.pop("__flat__")
+    named = dict(gen.named_parameters())
+    assert set(grads) == set(named)
+    spans = []
+    for n, p in named.items():
+        v = grads[n]
+        assert v.shape == p.shape and v.dtype == torch.float32
+        off = (v.data_ptr() - flat.data_ptr())
+        assert off % 256 == 0, n
+        spans.append((off // 4, off // 4 + p.numel()))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    assert spans[-1][1] <= flat.numel() < spans[-1][1] + 64
+    flat.fill_(1.0)
+    assert all(float(grads[n].sum()) == named[n].numel() for n in named)
