@@ -49,7 +49,7 @@ def build_parser(eval_mode=False):
     if eval_mode:
         p.add_argument('--cycles', type=int, default=1)
         p.add_argument('--finetune', action='store_true', default=False)
-        p.add_argument('--finetune_epochs', type=int, default=10)
+        p.add_argument('--finetune_epochs', type=int, default=100)
     p.add_argument('--warmup', type=float, default=0.2)
     p.add_argument('--lr', type=float, default=0.001)
     p.add_argument('--lr_type', type=str, default='cosine')

@@ -53,3 +53,30 @@ def test_huffman_avg_bits():
     assert n == len(vals) and abs(avg - expect / 5000) < 1e-12
     p = counts.double() / counts.sum()
     assert avg >= float(-(p * p.log2()).sum()) - 1e-9
+
+
+def _reference_cli():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "cli_flags.json")) as f:
+        return json.load(f)
+
+
+def test_every_reference_flag_exists_with_the_same_default():
+    """tests/golden/cli_flags.json is the argparse surface of the unmodified reference (main_train.py / main_eval.py,
+    extracted by tests/golden/make_cli_golden.py).  The mirrored parsers must know every flag (long and short
+    spelling) and give it the reference default."""
+    ref = _reference_cli()
+    for script, eval_mode in (("main_train.py", False), ("main_eval.py", True)):
+        parser = build_parser(eval_mode=eval_mode)
+        known = {s: a for a in parser._actions for s in a.option_strings}
+        for spec in ref[script]:
+            for flag in spec['flags']:
+                assert flag in known, (script, flag)
+            act = known[spec['flags'][-1]]
+            if 'default' in spec and not isinstance(spec['default'], str):
+                assert act.default == spec['default'], (script, spec['flags'], act.default, spec['default'])
+            elif spec.get('action') == 'store_true':
+                assert act.default is False and act.nargs == 0, (script, spec['flags'])
+            if 'nargs' in spec:
+                assert act.nargs == spec['nargs'], (script, spec['flags'])
