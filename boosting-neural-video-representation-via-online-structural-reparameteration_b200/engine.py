@@ -127,7 +127,7 @@ class NetExecutor:
 
         # ---- per block weights / gradient staging ------------------------------------------------
         self.K, self.bias, self.T, self.wf, self.wd, self.bias_p = [], [], [], [], [], []
-        self.dKp, self.dbias_p, self.dK, self.dbias, self.dT = [], [], [], [], []
+        self.dKp, self.dbias_p, self.dK, self.dbias, self.dT, self.dKb = [], [], [], [], [], []
         # the wgrad kernels accumulate (red.global.add) into dKp / dbias_p: all of them live in one pool that a
         # single memset clears per step
         pool_off, total = [], 0
@@ -148,11 +148,16 @@ class NetExecutor:
             if train:
                 self.dKp.append(self._wgrad_pool[off_k:off_k + g.nk * 9 * g.cpi].view(g.nk, 9, g.cpi))
                 self.dbias_p.append(self._wgrad_pool[off_b:off_b + g.nk])
-                self.dK.append(zeros(g.cout, g.cin, 3, 3))
-                self.dbias.append(zeros(g.cout))
+                # dK | dbias of a block live in ONE buffer: it is the block's gradient-exchange bucket (SURVEY.md 8e
+                # option 2: all-reduce the folded-kernel gradient, then run the linear fold backward on every rank)
+                nK = g.cout * g.cin * 9
+                bucket = zeros(nK + g.cout)
+                self.dKb.append(bucket)
+                self.dK.append(bucket[:nK].view(g.cout, g.cin, 3, 3))
+                self.dbias.append(bucket[nK:])
                 self.dT.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
             else:
-                for lst in (self.dKp, self.dbias_p, self.dK, self.dbias, self.dT):
+                for lst in (self.dKp, self.dbias_p, self.dK, self.dbias, self.dT, self.dKb):
                     lst.append(None)
 
         # ---- plans -----------------------------------------------------------------------------
@@ -293,10 +298,16 @@ class NetExecutor:
         return self.img
 
     # ------------------------------------------------------------------------------------ backward
-    def backward(self, gimg, grads, block_hook=None):
+    def backward(self, gimg, grads, block_hook=None, reduce=None):
         """Backward of `forward`. `grads` maps parameter name -> fp32 gradient tensor; every tensor must be
         zero on entry (the kernels accumulate into the ERB branch / stem / head gradients and overwrite the
         single-branch conv gradients).
+
+        reduce(t), if given (data-parallel fitting), sums the fp32 tensor `t` over the ranks in place on the current
+        stream.  It is called once per exchange bucket as soon as that bucket is complete — head gradients after the
+        head backward, each block's folded-kernel gradient `dK|dbias` right after its wgrad on the block's side stream
+        (the linear fold backward then runs on the summed dK on every rank), stem gradients at the end — so the
+        exchange overlaps the remaining dgrad chain.
 
         block_hook(l), if given, is called on block l's side stream once that block's parameter gradients are
         complete AND its dgrad has been issued (nothing in this backward reads the block's weights, packed operands
@@ -322,6 +333,15 @@ class NetExecutor:
                 ptr(gimg), ptr(self.img), ptr(self.x[self.L]), ptr(self.d[self.L]), self.B, self.H, self.W,
                 self.C_last, gL.cpo, ptr(head.weight), 1 if gen.sigmoid else 0, ptr(grads[hname + ".weight"]),
                 ptr(grads[hname + ".bias"]), ptr(self.dz[self.L]), st), "onr_head_bwd")
+            if reduce is not None:
+                head_done = torch.cuda.Event()
+                head_done.record(main)
+                with torch.cuda.stream(hside):
+                    hside.wait_event(head_done)
+                    reduce(self._flat_span(grads, [hname + ".weight", hname + ".bias"]))
+                    ev = torch.cuda.Event()
+                    ev.record(hside)
+                    joins.append(ev)
         else:
             # split: the reduction on a side stream, only dz on the critical path
             with torch.cuda.stream(hside):
@@ -329,6 +349,8 @@ class NetExecutor:
                     ptr(gimg), ptr(self.img), ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
                     1 if gen.sigmoid else 0, ptr(grads[hname + ".weight"]), ptr(grads[hname + ".bias"]),
                     _lib.stream()), "onr_head_bwd_gw")
+                if reduce is not None:
+                    reduce(self._flat_span(grads, [hname + ".weight", hname + ".bias"]))
                 ev = torch.cuda.Event()
                 ev.record(hside)
                 joins.append(ev)
@@ -359,6 +381,9 @@ class NetExecutor:
                     dK, db = grads[name + ".weight"], grads[name + ".bias"]
                 check(lib.onr_unpack_wgrad(ptr(self.dKp[l]), ptr(self.dbias_p[l]), g.cin, g.cnew, g.s,
                                            ptr(dK), ptr(db), sst), "onr_unpack_wgrad")
+                if reduce is not None:
+                    reduce(self.dKb[l] if blk.is_erb_train() else
+                           self._flat_span(grads, [name + ".weight", name + ".bias"]))
                 if blk.is_erb_train():
                     self.scatter_block_grads(l, grads)
                 ev = torch.cuda.Event()
@@ -382,8 +407,18 @@ class NetExecutor:
             ptr(lin2.weight), gen.fc_dim, gen.fc_h, gen.fc_w, g0.cpi,
             ptr(grads["stem.0.weight"]), ptr(grads["stem.0.bias"]),
             ptr(grads["stem.2.weight"]), ptr(grads["stem.2.bias"]), ptr(self.dh1), st), "onr_stem_bwd")
+        if reduce is not None:
+            reduce(self._flat_span(grads, ["stem.0.weight", "stem.0.bias", "stem.2.weight", "stem.2.bias"]))
         for ev in joins:
             main.wait_event(ev)
+
+    @staticmethod
+    def _flat_span(grads, names):
+        """The slice of the flat gradient buffer that covers the (consecutive) parameters `names`."""
+        flat, offs = grads["__flat__"], grads["__offsets__"]
+        lo = min(offs[n][0] for n in names)
+        hi = max(offs[n][0] + offs[n][1] for n in names)
+        return flat[lo:hi]
 
     def scatter_block_grads(self, l, grads):
         """dK/dbias of ERB block l -> gradients of its nine branch tensors (fold backward)."""

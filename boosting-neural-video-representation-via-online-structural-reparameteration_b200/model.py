@@ -295,11 +295,13 @@ class Generator(nn.Module):
         align = 64
         total = sum(-(-p.numel() // align) * align for _, p in named)
         flat = torch.zeros(total, dtype=torch.float32, device=named[0][1].device)
-        grads, off = {}, 0
+        grads, offsets, off = {}, {}, 0
         for n, p in named:
             grads[n] = flat[off:off + p.numel()].view_as(p)
+            offsets[n] = (off, p.numel())
             off += -(-p.numel() // align) * align
         grads["__flat__"] = flat
+        grads["__offsets__"] = offsets
         return grads
 
     def __deepcopy__(self, memo):

@@ -72,6 +72,14 @@ class FrameFitter:
         in_blocks = {id(p) for ps in self._block_params for p in ps}
         self._rest_params = [p for _, p in named if id(p) not in in_blocks]
         self._weights_valid = False
+        # Gradient exchange (world > 1).  "bucket" (default): per-block all-reduce of the folded-kernel gradients
+        # dK|dbias (12.8 MB at S720 instead of the 30 MB of branch gradients) issued on the block's side stream as soon
+        # as its wgrad is done, head / stem gradients as their own buckets; everything, NCCL calls included, is
+        # captured in ONE CUDA graph.  "flat" (ONR_DP_EXCHANGE=flat): round 1's single all-reduce of the whole flat
+        # buffer after the backward, kept for A/B timing.
+        self.exchange = os.environ.get("ONR_DP_EXCHANGE", "bucket")
+        if self.exchange not in ("bucket", "flat"):
+            raise ValueError("ONR_DP_EXCHANGE must be bucket or flat")
         self.graph = None
         self.use_graph = use_graph and self.device_sched
         self.host_step = 0
@@ -80,9 +88,14 @@ class FrameFitter:
     # ------------------------------------------------------------------------------------------
     def _body(self):
         self._body_pre()
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad)          # NCCL over NVLink; averaged by grad_scale inside Adam
+        if self.world > 1 and self.exchange == "flat":
+            dist.all_reduce(self.flat_grad)          # one exposed all-reduce of every branch gradient (round-1 scheme)
         self._body_post()
+
+    def _reduce(self, t):
+        """Gradient exchange of one bucket: NCCL all-reduce (sum) over NVLink on the current (side) stream; the
+        average is applied as grad_scale = 1/world inside the fused Adam kernel."""
+        dist.all_reduce(t)
 
     def _body_pre(self):
         """frame conversion, forward, loss + its gradient, backward -> local gradients in self.flat_grad"""
@@ -109,7 +122,8 @@ class FrameFitter:
                                      ptr(self.loss_work), _lib.stream()), "onr_msssim")
                 ms_done = torch.cuda.Event()
                 ms_done.record(self._ms_stream)
-        self.ex.backward(self.gimg, self.grads, block_hook=self._update_block if self.fold_ahead else None)
+        self.ex.backward(self.gimg, self.grads, block_hook=self._update_block if self.fold_ahead else None,
+                         reduce=self._reduce if (self.world > 1 and self.exchange == "bucket") else None)
         if ms_done is not None:
             torch.cuda.current_stream().wait_event(ms_done)
 
@@ -170,11 +184,6 @@ class FrameFitter:
             if self.graph is None:
                 self._capture()
             self.graph.replay()
-            if self.world > 1:
-                # the collective stays outside the graphs: graph 1 = up to the local gradients, eager NCCL
-                # all-reduce, graph 2 = schedule tick + Adam + metrics
-                dist.all_reduce(self.flat_grad)
-                self.graph_post.replay()
             self.opt._step_count_host += 1
         else:
             self._body()
@@ -213,14 +222,14 @@ class FrameFitter:
         if self.world == 1:
             with torch.cuda.graph(g):
                 self._body()
-            self.graph_post = None
         else:
-            with torch.cuda.graph(g):
-                self._body_pre()
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                self._body_post()
-            self.graph_post = g2
+            # the NCCL all-reduces are captured with the kernels (NCCL >= 2.9.6 supports stream capture; every rank
+            # captures and replays the same sequence).  thread_local mode: the process group's watchdog thread may
+            # touch the CUDA API while this thread captures.
+            dist.barrier()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._body()
         # the capture pass itself did not execute; fix the host-side counter it advanced
         self.opt._step_count_host = self.host_step
         self.graph = g

@@ -6,8 +6,11 @@ A plain restatement, on the CPU, of the reference's arithmetic for the frame-fit
 baseline — the product path (package dir + liborepnerv.so) never touches it.
 
 Each function cites the reference file:line (under /root/reference) it restates.  It is written with
-torch CPU tensor ops (fp32 by default, any dtype accepted so tests can run it in fp64), no autograd
+plain torch tensor ops (fp32 by default, any dtype accepted so tests can run it in fp64), no autograd
 tricks beyond `torch.autograd.grad` through the restated forward, and no import of the reference.
+The functions are device-agnostic: `tests/` also runs them on CUDA tensors with TF32 switched off
+(`torch.backends.cudnn.allow_tf32 = False`) as the full-size fp32 GPU oracle of SURVEY.md 8c-iv — still
+library (cuDNN/cuBLAS fp32) arithmetic of the restated algorithm, never the product kernels.
 
 Pinning: `tests/golden/make_golden.py` imports the UNMODIFIED reference `model.py` / `utils.py` in the
 build container and stores small input/output vectors in `tests/golden/*.pt`; `tests/test_oracle_golden.py`
@@ -128,7 +131,7 @@ def _gauss_1d(size=11, sigma=1.5, dtype=torch.float32):
 def _gauss_filter(x, win):
     """pytorch_msssim 0.2.1 `gaussian_filter`: separable VALID filtering, H pass then W pass, per channel."""
     C = x.shape[1]
-    w = win.to(x.dtype).view(1, 1, -1)
+    w = win.to(device=x.device, dtype=x.dtype).view(1, 1, -1)
     out = F.conv2d(x, w.view(1, 1, -1, 1).expand(C, 1, -1, 1), groups=C)
     return F.conv2d(out, w.view(1, 1, 1, -1).expand(C, 1, 1, -1), groups=C)
 
@@ -154,7 +157,7 @@ def ssim(X, Y):
 
 def ms_ssim(X, Y):
     """pytorch_msssim.ms_ssim(X, Y, data_range=1, size_average=True) as called at reference utils.py:205."""
-    weights = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], dtype=X.dtype)
+    weights = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], dtype=X.dtype, device=X.device)
     mcs = []
     for i in range(5):
         m, cs = ssim_maps(X, Y)

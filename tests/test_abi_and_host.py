@@ -130,7 +130,9 @@ def test_flat_gradient_buffer_is_aligned_and_complete(golden):
     _, gen = build(g, "ERB")
     grads = gen.alloc_grads()
     flat = grads.pop("__flat__")
+    offsets = grads.pop("__offsets__")
     named = dict(gen.named_parameters())
+    assert all(offsets[n] == ((grads[n].data_ptr() - flat.data_ptr()) // 4, named[n].numel()) for n in named)
     assert set(grads) == set(named)
     spans = []
     for n, p in named.items():
