@@ -82,6 +82,8 @@ _SIGNATURES = {
     "onr_head_bwd_gw": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "onr_loss_workspace_bytes": (sz, [i32, i32, i32]),
     "onr_fusion6_fwd_bwd": (i32, [vp, vp, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp]),
+    "onr_fusion_loss": (i32, [vp, vp, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp, vp]),
+    "onr_scale_by_device_scalar": (i32, [vp, sz, vp, vp]),
     "onr_msssim_workspace_bytes": (sz, [i32, i32, i32]),
     "onr_msssim": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "onr_adam_block_elems": (sz, []),

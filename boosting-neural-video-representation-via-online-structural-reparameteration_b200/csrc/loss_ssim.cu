@@ -178,7 +178,7 @@ ssim_stats_kernel(const Gauss gw, const float* __restrict__ X, const float* __re
 // grid (tiles_x, tiles_y, planes) over INPUT pixels. gacc[0] += sum |d|, gacc[1] += sum d^2.
 __global__ void __launch_bounds__(256)
 fusion_bwd_kernel(const Gauss gw, const float* __restrict__ X, const float* __restrict__ Y, int H, int W,
-                  const float* __restrict__ coef, int planes, float k_l1, float k_ssim,
+                  const float* __restrict__ coef, int planes, float k_l1, float k_ssim, float k_mse,
                   float* __restrict__ grad, double* __restrict__ gacc) {
     __shared__ float sc[3][kIn][kPitch];
     __shared__ float sv[3][kTS][kPitch];
@@ -258,7 +258,8 @@ fusion_bwd_kernel(const Gauss gw, const float* __restrict__ X, const float* __re
             l2 = fmaf(d, d, l2);
             if (grad) {
                 const float sgn = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f);
-                grad[idx] = k_l1 * sgn + k_ssim * (acc[o][0] + 2.0f * xv * acc[o][1] + yv * acc[o][2]);
+                const float g = k_l1 * sgn + k_ssim * (acc[o][0] + 2.0f * xv * acc[o][1] + yv * acc[o][2]);
+                grad[idx] = k_mse != 0.0f ? fmaf(k_mse, d, g) : g;   // k_mse == 0 keeps the Fusion6 bits unchanged
             }
         }
     }
@@ -272,18 +273,29 @@ fusion_bwd_kernel(const Gauss gw, const float* __restrict__ X, const float* __re
 
 __global__ void fusion_finalize_kernel(const double* __restrict__ gacc, const double* __restrict__ plane_acc,
                                        int planes, double n_all, double n_valid, float w_l1, float w_ssim,
-                                       float* __restrict__ out5) {
+                                       float w_mse, float* __restrict__ out5) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double s = 0.0;
     for (int p = 0; p < planes; ++p) s += plane_acc[p * 2] / n_valid;
     const double ssim = s / planes;
     const double l1 = gacc[0] / n_all;
     const double mse = gacc[1] / n_all;
-    out5[0] = (float)(w_l1 * l1 + w_ssim * (1.0 - ssim));
+    out5[0] = (float)(w_l1 * l1 + w_ssim * (1.0 - ssim) + w_mse * mse);
     out5[1] = (float)l1;
     out5[2] = (float)ssim;
     out5[3] = (float)mse;
     out5[4] = (float)(-10.0 * log10(mse));
+}
+
+__global__ void scale_by_device_scalar_kernel(float4* __restrict__ x, size_t n4, float* __restrict__ tail, int ntail,
+                                              const float* __restrict__ s) {
+    const float k = __ldg(s);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = x[i];
+        v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+        x[i] = v;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] *= k;
 }
 
 // avg_pool2d(kernel 2, stride 2, padding (ph, pw), count_include_pad) of both images of a scale in one launch
@@ -350,9 +362,27 @@ size_t onr_loss_workspace_bytes(int B, int H, int W) {
            3 * planes * Hv * Wv * sizeof(float);
 }
 
+int onr_scale_by_device_scalar(float* x, size_t n, const float* scalar_dev, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(((uintptr_t)x & 15) == 0, "scale: x must be 16-byte aligned");
+    const size_t n4 = n / 4;
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    if (grid < 1) grid = 1;
+    scale_by_device_scalar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(x), n4, x + n4 * 4,
+                                                                          (int)(n - n4 * 4), scalar_dev);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
+
 int onr_fusion6_fwd_bwd(const float* pred, const float* target, int B, int H, int W, float w_l1,
                         float w_ssim, float grad_scale, float* out5, float* grad_pred, void* work,
                         void* stream) {
+    return onr_fusion_loss(pred, target, B, H, W, w_l1, 0.0f, w_ssim, grad_scale, out5, grad_pred, work, stream);
+}
+
+int onr_fusion_loss(const float* pred, const float* target, int B, int H, int W, float w_l1, float w_mse,
+                    float w_ssim, float grad_scale, float* out5, float* grad_pred, void* work, void* stream) {
     using namespace onr;
     ONR_REQUIRE(H > kHalo && W > kHalo, "fusion6: image smaller than the 11x11 SSIM window");
     const Gauss gw = make_gauss();
@@ -373,10 +403,11 @@ int onr_fusion6_fwd_bwd(const float* pred, const float* target, int B, int H, in
     const double n_all = (double)planes * H * W, n_valid = (double)Hv * Wv;
     const float k_l1 = (float)(w_l1 / n_all) * grad_scale;
     const float k_ssim = (float)(-(double)w_ssim / (n_valid * planes)) * grad_scale;
+    const float k_mse = (float)(2.0 * (double)w_mse / n_all) * grad_scale;
     dim3 g2(ceil_div(W, kTS), ceil_div(H, kTS), planes);
-    fusion_bwd_kernel<<<g2, 256, 0, st>>>(gw, pred, target, H, W, coef, planes, k_l1, k_ssim, grad_pred, gacc);
+    fusion_bwd_kernel<<<g2, 256, 0, st>>>(gw, pred, target, H, W, coef, planes, k_l1, k_ssim, k_mse, grad_pred, gacc);
     ONR_LAUNCH_CHECK();
-    fusion_finalize_kernel<<<1, 32, 0, st>>>(gacc, pacc, planes, n_all, n_valid, w_l1, w_ssim, out5);
+    fusion_finalize_kernel<<<1, 32, 0, st>>>(gacc, pacc, planes, n_all, n_valid, w_l1, w_ssim, w_mse, out5);
     ONR_LAUNCH_CHECK();
     return 0;
 }

@@ -123,7 +123,8 @@ class NetExecutor:
             # x[0]/d[0] come from the stem kernel which always writes both
             self.d.append(zeros(B, hh, ww, cp, dtype=bf16) if (train or l == 0) else None)
             self.dz.append(zeros(B, hh, ww, cp, dtype=bf16) if train else None)
-        self.img = zeros(B, 3, self.H, self.W)
+        self._img_static = zeros(B, 3, self.H, self.W)      # CUDA-graph paths always decode into this one
+        self.img = self._img_static
 
         # ---- per block weights / gradient staging ------------------------------------------------
         self.K, self.bias, self.T, self.wf, self.wd, self.bias_p = [], [], [], [], [], []
@@ -222,6 +223,10 @@ class NetExecutor:
                 ts = ([conv.weight_orig, conv.weight_mask] if hasattr(conv, "weight_orig") else [conv.weight])
                 ts.append(conv.bias)
             key += [(t.data_ptr(), t._version) for t in ts]
+        for lin in (self.gen.stem[0], self.gen.stem[2]):
+            # pruned stem layers (main_eval.py:572-587) carry weight_orig / weight_mask; `.weight` is derived
+            ts = [lin.weight_orig, lin.weight_mask] if hasattr(lin, "weight_orig") else [lin.weight]
+            key += [(t.data_ptr(), t._version) for t in ts]
         # FrameFitter updates parameters through raw pointers inside a CUDA graph (no per-tensor version bump): it
         # advances this counter instead
         key.append(getattr(self.gen, "_weights_epoch", 0))
@@ -262,9 +267,11 @@ class NetExecutor:
             "onr_pack_weights")
 
     # ------------------------------------------------------------------------------------- forward
-    def forward(self, embed=None, t_norm=None, freqs=None, refresh=True):
-        """Runs the decoder; returns the image buffer [B,3,H,W] fp32 (owned by the executor).
+    def forward(self, embed=None, t_norm=None, freqs=None, refresh=True, out=None):
+        """Runs the decoder; returns the image [B,3,H,W] fp32: `out` when given (it then also becomes the image the
+        next `backward` differentiates through), else the executor's own static buffer.
         Either `embed` [B,2L] (reference entry) or `t_norm` [B] + `freqs` [L] (fused PE) is given."""
+        self.img = out if out is not None else self._img_static
         gen, st = self.gen, _lib.stream()
         lin1, lin2 = gen.stem[0], gen.stem[2]
         g0 = self.geoms[0]
@@ -273,6 +280,13 @@ class NetExecutor:
             key = self._weights_key()
             refresh = key != getattr(self, "_packed_key", None)
             self._packed_key = key
+        if refresh or self.train:
+            # torch.nn.utils.prune recomputes `.weight = weight_orig * weight_mask` in a forward-pre-hook; the stem
+            # Linear modules are never called here, so run their hooks by hand (the reference re-evaluates them on
+            # every forward, main_eval.py:572-587 + model.py:612)
+            for lin in (lin1, lin2):
+                for hook in lin._forward_pre_hooks.values():
+                    hook(lin, None)
         events = self.refresh_weights() if refresh else None     # forks side streams first
         if t_norm is None:
             if embed is None:

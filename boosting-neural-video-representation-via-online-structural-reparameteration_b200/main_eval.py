@@ -48,6 +48,91 @@ def global_prune(model, amount):
     return zeros, total
 
 
+def prune_and_quantise(model, args, n_frames, frame_hw, log_bpp=None):
+    """Steps 2-3 of the reference flow on a loaded deploy / vanilla model: global magnitude pruning
+    (main_eval.py:572-587) then quantisation of every state-dict tensor + Huffman / bpp statistics (:652-729)
+    and `load_state_dict` (:703).  Returns the info text the reference writes to its `only_prune*` file."""
+    info = ''
+    if args.prune_ratio < 1:
+        zeros, total = global_prune(model, args.prune_ratio)
+        msg = f'global prune: target {args.prune_ratio}, actual {zeros / total:.3f} ({zeros}/{total} mask zeros)'
+        print(msg)
+        info += msg + '\n'
+    if args.quant_bit != -1:
+        with torch.no_grad():
+            cur = model.state_dict()
+            symbols = []
+            for k, v in cur.items():
+                large = v.dim() in {2, 4} and 'bias' not in k
+                q, new_v = quantize_per_tensor(v, args.quant_bit, args.quant_axis if large else -1)
+                symbols.append(q[v != 0].flatten())
+                cur[k] = new_v.to(v.device).type_as(v)
+            avg_bits, total_bits, n_sym = huffman_avg_bits(torch.cat(symbols))
+            model.load_state_dict(cur)
+            H, W = frame_hw
+            bpp = total_bits / (n_frames * H * W)
+            msg = (f'quantised {len(symbols)} tensors to {args.quant_bit} bit; Huffman {avg_bits:.4f} bit/symbol over '
+                   f'{n_sym} symbols, efficiency {avg_bits / args.quant_bit:.4f}; total {int(total_bits)} bits, '
+                   f'{n_frames} frames {H}x{W}, BPP={bpp:.6f}')
+            print(msg)
+            info += msg + '\n'
+            if log_bpp:
+                with open(log_bpp, 'a') as f:
+                    f.write(msg + '\n')
+    return info
+
+
+def decode_clip(model, pe, cache, args, log_path=None, local_rank=0, fwd_num=10, quiet=False):
+    """The reference decode loop (main_eval.py:738-827): per frame `fwd_num` timed forwards (host clock around
+    `torch.cuda.synchronize()`, as the reference times it), on the first frame 5 + 50 extra forwards for the
+    "first frame FPS", PSNR / MS-SSIM accumulation, optional PNG dump.
+    Returns dict(psnr, msssim, fps, fps_first_frame, frames)."""
+    psnrs, msssims, times = [], [], []
+    model.eval()
+    eval_str, fps0 = '', None
+    with torch.no_grad():
+        for i in range(len(cache)):
+            embed = pe(cache.t[i:i + 1])
+            target = cache.frames[i:i + 1].float().div(255)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for _ in range(fwd_num):
+                out = model(embed)
+            torch.cuda.synchronize()
+            times.append(time.time() - t0)
+            if i == 0:
+                for _ in range(5):
+                    model(embed)
+                torch.cuda.synchronize()
+                t0 = time.time()
+                for _ in range(50):
+                    model(embed)
+                torch.cuda.synchronize()
+                fps0 = 50 / (time.time() - t0)
+                eval_str = f'[first frame] FPS: {fps0:.2f}\n'
+                if not quiet:
+                    print(eval_str.strip())
+            if getattr(args, 'dump_images', False):
+                from torchvision.utils import save_image
+                vis = f'{args.outf}/visualize'
+                os.makedirs(vis, exist_ok=True)
+                save_image(out[-1][0], f'{vis}/pred_{i}.png')
+            psnrs.append(frame_stats(out[0], target)[4].view(1))
+            msssims.append(msssim_fn(out, [target]).view(1))
+            if i % args.print_freq == 0 or i == len(cache) - 1:
+                fps = fwd_num * (i + 1) / sum(times)
+                print_str = 'Rank:{}, Step [{}/{}], PSNR: {}, MSSSIM: {} FPS: {}'.format(
+                    local_rank, i + 1, len(cache), RoundTensor(torch.cat(psnrs).mean().view(1), 2, False),
+                    RoundTensor(torch.cat(msssims).mean().view(1), 4, False), round(fps, 2))
+                if not quiet:
+                    print(print_str)
+                if log_path:
+                    with open(log_path, 'a') as f:
+                        f.write(print_str + '\n' + eval_str + '\n')
+    return dict(psnr=torch.cat(psnrs).mean().item(), msssim=torch.cat(msssims).mean().item(),
+                fps=fwd_num * len(cache) / sum(times), fps_first_frame=fps0, frames=len(cache))
+
+
 def main(argv=None):
     args = finish_args(build_parser(eval_mode=True).parse_args(argv))
     if args.finetune:
@@ -73,80 +158,18 @@ def main(argv=None):
     model.load_state_dict(strip_profiler_keys(state), strict=False)
     info += f'loaded {path}\n'
 
-    if args.prune_ratio < 1:
-        zeros, total = global_prune(model, args.prune_ratio)
-        msg = f'global prune: target {args.prune_ratio}, actual {zeros / total:.3f} ({zeros}/{total} mask zeros)'
-        print(msg)
-        info += msg + '\n'
-
     cache = FrameCache(args.dataset, device, vid_list=args.vid, frame_gap=args.test_gap)
-
-    if args.quant_bit != -1:
-        with torch.no_grad():
-            cur = model.state_dict()
-            symbols = []
-            for k, v in cur.items():
-                large = v.dim() in {2, 4} and 'bias' not in k
-                q, new_v = quantize_per_tensor(v, args.quant_bit, args.quant_axis if large else -1)
-                symbols.append(q[v != 0].flatten())
-                cur[k] = new_v.to(v.device).type_as(v)
-            avg_bits, total_bits, n_sym = huffman_avg_bits(torch.cat(symbols))
-            model.load_state_dict(cur)
-            H, W = cache.frames.shape[-2:]
-            bpp = total_bits / (len(cache) * H * W)
-            msg = (f'quantised {len(symbols)} tensors to {args.quant_bit} bit; Huffman {avg_bits:.4f} bit/symbol over '
-                   f'{n_sym} symbols, efficiency {avg_bits / args.quant_bit:.4f}; total {int(total_bits)} bits, '
-                   f'{len(cache)} frames {H}x{W}, BPP={bpp:.6f}')
-            print(msg)
-            info += msg + '\n'
-            with open('{}/bpp_rank{}.txt'.format(args.outf, local_rank), 'a') as f:
-                f.write(msg + '\n')
+    info += prune_and_quantise(model, args, len(cache), tuple(cache.frames.shape[-2:]),
+                               log_bpp='{}/bpp_rank{}.txt'.format(args.outf, local_rank)
+                               if args.quant_bit != -1 else None)
 
     only_name = 'only_prune{:.2f}_quant{}.txt'.format(args.prune_ratio, args.quant_bit if args.quant_bit > 0 else 'full')
-    with open('{}/{}'.format(args.outf, only_name), 'w', encoding='utf-8') as f:
+    log_path = '{}/{}'.format(args.outf, only_name)
+    with open(log_path, 'w', encoding='utf-8') as f:
         f.write(info)
-
-    fwd_num = getattr(args, 'fwd_num', 10)
-    psnrs, msssims, times = [], [], []
-    model.eval()
-    eval_str = ''
-    with torch.no_grad():
-        for i in range(len(cache)):
-            embed = pe(cache.t[i:i + 1])
-            target = cache.frames[i:i + 1].float().div(255)
-            torch.cuda.synchronize()
-            t0 = time.time()
-            for _ in range(fwd_num):
-                out = model(embed)
-            torch.cuda.synchronize()
-            times.append(time.time() - t0)
-            if i == 0:
-                for _ in range(5):
-                    model(embed)
-                torch.cuda.synchronize()
-                t0 = time.time()
-                for _ in range(50):
-                    model(embed)
-                torch.cuda.synchronize()
-                fps0 = 50 / (time.time() - t0)
-                eval_str = f'[first frame] FPS: {fps0:.2f}\n'
-                print(eval_str.strip())
-            if args.dump_images:
-                from torchvision.utils import save_image
-                vis = f'{args.outf}/visualize'
-                os.makedirs(vis, exist_ok=True)
-                save_image(out[-1][0], f'{vis}/pred_{i}.png')
-            psnrs.append(frame_stats(out[0], target)[4].view(1))
-            msssims.append(msssim_fn(out, [target]).view(1))
-            if i % args.print_freq == 0 or i == len(cache) - 1:
-                fps = fwd_num * (i + 1) / sum(times)
-                print_str = 'Rank:{}, Step [{}/{}], PSNR: {}, MSSSIM: {} FPS: {}'.format(
-                    local_rank, i + 1, len(cache), RoundTensor(torch.cat(psnrs).mean().view(1), 2, False),
-                    RoundTensor(torch.cat(msssims).mean().view(1), 4, False), round(fps, 2))
-                print(print_str)
-                with open('{}/{}'.format(args.outf, only_name), 'a') as f:
-                    f.write(print_str + '\n' + eval_str + '\n')
-    return torch.cat(psnrs).mean().item(), torch.cat(msssims).mean().item()
+    res = decode_clip(model, pe, cache, args, log_path=log_path, local_rank=local_rank,
+                      fwd_num=getattr(args, 'fwd_num', 10))
+    return res['psnr'], res['msssim']
 
 
 if __name__ == '__main__':

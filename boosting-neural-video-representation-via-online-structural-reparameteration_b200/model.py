@@ -221,20 +221,39 @@ class NeRVBlock(nn.Module):
 
 
 class _GeneratorFunction(torch.autograd.Function):
-    """Whole-decoder autograd node: forward = executor.forward, backward = executor.backward."""
+    """Whole-decoder autograd node: forward = executor.forward, backward = executor.backward.
+
+    The image is written straight into a fresh tensor (no copy).  The backward writes the parameter gradients into
+    the Generator's PERSISTENT flat gradient buffer and binds `p.grad` to views of it, so the reference loop
+    (`optimizer.zero_grad(); loss.backward(); optimizer.step()`, main_train.py:248-250) costs one memset and no
+    per-step allocation; only a second backward without zero_grad in between (gradient accumulation) takes the
+    generic path that hands temporaries to autograd."""
 
     @staticmethod
     def forward(ctx, gen, ex, embed, *params):
-        img = ex.forward(embed=embed)
+        img = torch.empty(ex.B, 3, ex.H, ex.W, dtype=torch.float32, device=ex.dev)
+        ex.forward(embed=embed, out=img)
         ctx.gen, ctx.ex = gen, ex
-        return img.clone()
+        return img
 
     @staticmethod
     def backward(ctx, gimg):
         gen, ex = ctx.gen, ctx.ex
+        named = list(gen.named_parameters())
+        pg = gen.persistent_grads()
+        owned = [p.grad is pg[n] for n, p in named]
+        fast = all(p.requires_grad and (p.grad is None or o) for (n, p), o in zip(named, owned))
+        if fast and (gen._grads_clean or not any(owned)):
+            if not gen._grads_clean:
+                pg["__flat__"].zero_()
+            ex.backward(gimg.contiguous(), pg)
+            gen._grads_clean = False
+            for n, p in named:
+                p.grad = pg[n]
+            return (None, None, None) + (None,) * len(named)
         grads = gen.alloc_grads()
         ex.backward(gimg.contiguous(), grads)
-        out = [grads[n] if p.requires_grad else None for n, p in gen.named_parameters()]
+        out = [grads[n] if p.requires_grad else None for n, p in named]
         return (None, None, None) + tuple(out)
 
 
@@ -271,6 +290,8 @@ class Generator(nn.Module):
                                     if i == len(strides) - 1 else None)
         self.sigmoid = kargs['sigmoid']
         self._executors = {}
+        self._pgrads = None
+        self._grads_clean = False
 
     # ---- helpers for the executor ---------------------------------------------------------------
     def head_name(self):
@@ -304,6 +325,22 @@ class Generator(nn.Module):
         grads["__offsets__"] = offsets
         return grads
 
+    def persistent_grads(self):
+        """The flat gradient buffer `loss.backward()` writes into (allocated once per device; see
+        _GeneratorFunction).  `_grads_clean` tracks whether it is known to be all zeros."""
+        dev = next(self.parameters()).device
+        if self._pgrads is None or self._pgrads["__flat__"].device != dev:
+            self._pgrads = self.alloc_grads()
+            self._grads_clean = True
+            for n, p in self.named_parameters():
+                p._onr_grad_owner, p._onr_name = self, n
+        return self._pgrads
+
+    def zero_persistent_grads(self):
+        if self._pgrads is not None and not self._grads_clean:
+            self._pgrads["__flat__"].zero_()
+            self._grads_clean = True
+
     def __deepcopy__(self, memo):
         # executors hold raw device pointers / TMA descriptors of THIS model's buffers: never copy them
         # (reference main_train.py:332 deep-copies the model every epoch for the deploy checkpoint)
@@ -312,7 +349,13 @@ class Generator(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = {} if k == "_executors" else copy.deepcopy(v, memo)
+            if k == "_executors":
+                new.__dict__[k] = {}
+            elif k == "_pgrads":
+                new.__dict__[k] = None
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        new._grads_clean = False
         return new
 
     def forward(self, input):
@@ -325,5 +368,6 @@ class Generator(nn.Module):
             img = _GeneratorFunction.apply(self, ex, input.detach(), *params)
         else:
             with torch.no_grad():
-                img = ex.forward(embed=input).clone()
+                img = torch.empty(B, 3, ex.H, ex.W, dtype=torch.float32, device=ex.dev)
+                ex.forward(embed=input, out=img)
         return [img]

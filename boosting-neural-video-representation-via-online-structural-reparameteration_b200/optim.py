@@ -45,6 +45,29 @@ class FusedAdam(torch.optim.Optimizer):
         self._step_count_host = int(max(steps)) if steps else 0
         self._tables = {}
 
+    def zero_grad(self, set_to_none=True):
+        """torch.optim.Optimizer.zero_grad, except that gradients living in a Generator's persistent flat buffer
+        (bound to `p.grad` by `loss.backward()`, see model._GeneratorFunction) stay bound and are cleared with ONE
+        memset instead of being dropped and re-allocated every step (reference main_train.py:248)."""
+        owners = []
+        for group in self.param_groups:
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                owner = getattr(p, "_onr_grad_owner", None)
+                if owner is not None and owner._pgrads is not None and \
+                        p.grad.data_ptr() == owner._pgrads["__flat__"].data_ptr() + 4 * owner._pgrads["__offsets__"].get(
+                            getattr(p, "_onr_name", ""), (-1, 0))[0]:
+                    if all(owner is not o for o in owners):
+                        owners.append(owner)
+                elif set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.detach_()
+                    p.grad.zero_()
+        for owner in owners:
+            owner.zero_persistent_grads()
+
     # ---- table of raw pointers -------------------------------------------------------------------
     def _table(self, gi, group, subset=None):
         params = [p for p in (group['params'] if subset is None else subset) if p.grad is not None]

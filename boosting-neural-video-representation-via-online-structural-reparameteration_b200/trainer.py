@@ -17,7 +17,7 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import check, ptr
 from .optim import FusedAdam
-from .utils import _L1_SSIM_LOSSES, lr_multiplier
+from .utils import LOSS_TERMS, lr_multiplier
 
 
 class FrameFitter:
@@ -27,9 +27,9 @@ class FrameFitter:
         self.model, self.pe, self.args = model, pe, args
         self.world = world_size
         self.B = args.batchSize
-        if args.loss_type not in _L1_SSIM_LOSSES:
+        if args.loss_type not in LOSS_TERMS:
             raise NotImplementedError(f"loss_type {args.loss_type!r} is outside the B200 hot path")
-        self.w_l1, self.w_ssim = _L1_SSIM_LOSSES[args.loss_type]
+        self.w_l1, self.w_mse, self.w_ssim = LOSS_TERMS[args.loss_type]
         self.ex = model.executor(self.B, True)
         dev = self.ex.dev
         self.dev = dev
@@ -105,8 +105,8 @@ class FrameFitter:
             self._tick()        # the per-block Adam updates inside the backward need this step's lr / step count
         check(lib.onr_frame_u8_to_f32(ptr(self.frame_u8), self.frame_u8.numel(), ptr(self.target), st), "u8_to_f32")
         img = self.ex.forward(t_norm=self.t_norm, freqs=self.freqs, refresh=not self.fold_ahead)
-        check(lib.onr_fusion6_fwd_bwd(ptr(img), ptr(self.target), B, H, W, self.w_l1, self.w_ssim, 1.0,
-                                      ptr(self.out), ptr(self.gimg), ptr(self.loss_work), st), "onr_fusion6_fwd_bwd")
+        check(lib.onr_fusion_loss(ptr(img), ptr(self.target), B, H, W, self.w_l1, self.w_mse, self.w_ssim, 1.0,
+                                  ptr(self.out), ptr(self.gimg), ptr(self.loss_work), st), "onr_fusion_loss")
         ms_done = None
         if self.with_msssim:
             # the MS-SSIM metric (reference main_train.py:254) runs on a side stream, concurrently with the whole

@@ -181,6 +181,13 @@ size_t onr_loss_workspace_bytes(int B, int H, int W);
 int onr_fusion6_fwd_bwd(const float* pred, const float* target, int B, int H, int W,
                         float w_l1, float w_ssim, float grad_scale,
                         float* out5, float* grad_pred, void* work, void* stream);
+/* The general member of the family utils.py:142-166 spells out (L2, L1, SSIM, Fusion1..9):
+ * loss = w_l1 * mean|p-t| + w_mse * mean (p-t)^2 + w_ssim * (1 - SSIM); same outputs as above. */
+int onr_fusion_loss(const float* pred, const float* target, int B, int H, int W,
+                    float w_l1, float w_mse, float w_ssim, float grad_scale,
+                    float* out5, float* grad_pred, void* work, void* stream);
+/* x[0..n) *= *scalar_dev (autograd's upstream gradient of the loss, main_train.py:243-244, without a host sync). */
+int onr_scale_by_device_scalar(float* x, size_t n, const float* scalar_dev, void* stream);
 /* utils.py:201-211 / pytorch_msssim.ms_ssim: 5 scales, avg_pool2d(2, padding = dim%2). out[1]. */
 size_t onr_msssim_workspace_bytes(int B, int H, int W);
 int onr_msssim(const float* pred, const float* target, int B, int H, int W, float* out1,

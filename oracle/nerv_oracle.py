@@ -191,17 +191,22 @@ def ssim_direct_f64(X, Y):
     return m.mean()
 
 
-LOSS_WEIGHTS = {'L1': (1.0, 0.0), 'SSIM': (0.0, 1.0), 'Fusion2': (0.3, 0.7), 'Fusion4': (0.5, 0.5),
-                'Fusion6': (0.7, 0.3), 'Fusion9': (0.9, 0.1)}
+# loss_type -> weights of (mean |p-t|, mean (p-t)^2, 1 - SSIM): reference utils.py:142-166
+LOSS_WEIGHTS = {'L2': (0.0, 1.0, 0.0), 'L1': (1.0, 0.0, 0.0), 'SSIM': (0.0, 0.0, 1.0),
+                'Fusion1': (0.0, 0.3, 0.7), 'Fusion2': (0.3, 0.0, 0.7), 'Fusion3': (0.0, 0.5, 0.5),
+                'Fusion4': (0.5, 0.0, 0.5), 'Fusion5': (0.0, 0.7, 0.3), 'Fusion6': (0.7, 0.0, 0.3),
+                'Fusion7': (0.3, 0.7, 0.0), 'Fusion8': (0.5, 0.5, 0.0), 'Fusion9': (0.9, 0.0, 0.1)}
 
 
 def loss_fn(pred, target, loss_type='Fusion6'):
-    """reference utils.py:139-166 for the L1 / SSIM combinations."""
-    w_l1, w_ssim = LOSS_WEIGHTS[loss_type]
+    """reference utils.py:139-166 for the L1 / L2 / SSIM combinations."""
+    w_l1, w_mse, w_ssim = LOSS_WEIGHTS[loss_type]
     target = target.detach()
     loss = 0
     if w_l1:
         loss = loss + w_l1 * torch.mean(torch.abs(pred - target))
+    if w_mse:
+        loss = loss + w_mse * F.mse_loss(pred, target)
     if w_ssim:
         loss = loss + w_ssim * (1 - ssim(pred, target))
     return loss
@@ -286,3 +291,40 @@ def train_step(sd, opt_state, embed, target, cfg, lr, t, loss_type='Fusion6', be
         p, m, v = adam_step(params[n].detach(), g, m, v, t, lr, beta1=beta1)
         new_sd[n], new_state[n], gdict[n] = p, (m, v), g
     return new_sd, new_state, loss.detach(), img.detach(), gdict
+
+
+# ----------------------------------------------------------------------------- reference-shaped random state
+def random_state(cfg, w, seed=1, deploy=False, branch_type='ERB'):
+    """A random state dict with the reference's parameter names / shapes (model.py:571-609, :316-343) drawn from the
+    nn.Linear / nn.Conv2d default distribution U(-1/sqrt(fan_in), 1/sqrt(fan_in)) — for the timed CPU / library legs
+    of bench.py, which must not import the package.  cfg: dict(fc_h, fc_w, fc_dim, strides); w: dict(stem_dim_num,
+    expansion, reduction, lower_width).  `deploy` gives the single-branch layout (rbr_reparam)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def u(shape, fan_in):
+        b = 1.0 / math.sqrt(fan_in)
+        return (torch.rand(shape, generator=g) * 2 - 1) * b
+
+    stem_dim = int(str(w['stem_dim_num']).split('_')[0])
+    fd, fh, fw = cfg['fc_dim'], cfg['fc_h'], cfg['fc_w']
+    sd = {'stem.0.weight': u((stem_dim, 80), 80), 'stem.0.bias': u((stem_dim,), 80),
+          'stem.2.weight': u((fd * fh * fw, stem_dim), stem_dim), 'stem.2.bias': u((fd * fh * fw,), stem_dim)}
+    c = fd
+    for i, s in enumerate(cfg['strides']):
+        cnew = int(c * w['expansion']) if i == 0 else max(c // w['reduction'], w['lower_width'])
+        co, p = cnew * s * s, f'layers.{i}.'
+        if deploy:
+            sd[p + 'rbr_reparam.weight'], sd[p + 'rbr_reparam.bias'] = u((co, c, 3, 3), 9 * c), u((co,), 9 * c)
+        elif branch_type == 'NeRV_vanilla':
+            sd[p + 'branch.weight'], sd[p + 'branch.bias'] = u((co, c, 3, 3), 9 * c), u((co,), 9 * c)
+        else:
+            sd[p + 'rbr_3x3_branch.weight'], sd[p + 'rbr_3x3_branch.bias'] = u((co, c, 3, 3), 9 * c), u((co,), 9 * c)
+            sd[p + 'rbr_3x1_branch.weight'], sd[p + 'rbr_3x1_branch.bias'] = u((co, c, 3, 1), 3 * c), u((co,), 3 * c)
+            sd[p + 'rbr_1x3_branch.weight'], sd[p + 'rbr_1x3_branch.bias'] = u((co, c, 1, 3), 3 * c), u((co,), 3 * c)
+            sd[p + 'rbr_1x1_3x3_1x1_branch_1x1_1.weight'] = u((2 * c, c, 1, 1), c)
+            sd[p + 'rbr_1x1_3x3_1x1_branch_3x3.weight'] = u((co, 2 * c, 3, 3), 18 * c)
+            sd[p + 'rbr_1x1_3x3_1x1_branch_1x1_2.weight'] = u((co, co, 1, 1), co)
+        c = cnew
+    last = len(cfg['strides']) - 1
+    sd[f'head_layers.{last}.weight'], sd[f'head_layers.{last}.bias'] = u((3, c, 1, 1), c), u((3,), c)
+    return sd

@@ -230,7 +230,7 @@ def test_fusion6_forward_backward(dev, shape):
     g = torch.Generator().manual_seed(8)
     a = torch.rand(shape, generator=g)
     b = (a + 0.1 * torch.randn(shape, generator=g)).clamp(0, 1)
-    for lt in ("Fusion6", "L1", "SSIM"):
+    for lt in ("Fusion6", "L1", "SSIM", "L2", "Fusion1", "Fusion7"):
         p = a.clone().requires_grad_(True)
         ref = O.loss_fn(p, b, lt)
         ref.backward()
@@ -350,6 +350,19 @@ def test_eval_pipeline_prune_quant(dev, golden):
     with torch.no_grad():
         img_q = dep(embed)[0]
     assert torch.isfinite(img_q).all() and rel_l2(img_q, img_pruned) < 0.2
+    # what the reference decodes after load_state_dict (main_eval.py:703): every pruned module recomputes
+    # weight = weight_orig * weight_mask from the QUANTISED entries on its next forward — stem Linears included
+    sd_q = {}
+    for k, v in cur.items():
+        if k.endswith('weight_orig'):
+            sd_q[k[:-len('_orig')]] = (v * cur[k[:-len('orig')] + 'mask']).cpu()
+        elif not k.endswith('weight_mask'):
+            sd_q[k] = v.cpu()
+    img_ref_q = O.generator_forward(sd_q, O.pos_encoding(g['pos'], 1.25, 40), ocfg(g['cfg']))
+    assert rel_l2(img_q, img_ref_q) <= 1e-2
+    # A13 quirk: quantising weight_mask (min = max = 1 per row) turns every mask entry into 1
+    # (rows that were pruned completely keep their zeros)
+    assert all((v == 1).float().mean().item() > 0.99 for k, v in cur.items() if k.endswith('weight_mask'))
 
 
 # ------------------------------------------------------------------------------------------- full size
