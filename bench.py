@@ -622,7 +622,15 @@ def run_ours(opts):
                                               "(oracle port)"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the step graph holds captured NCCL kernels: release it before the communicator goes away
+        # (destroy_process_group otherwise blocks on the communicator the live graph still references)
         dist.barrier()
+        torch.cuda.synchronize()
+        fit.graph = None
+        del fit
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
