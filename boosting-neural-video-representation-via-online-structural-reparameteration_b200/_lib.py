@@ -60,6 +60,14 @@ _SIGNATURES = {
     "onr_stem_bwd": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "onr_erb_fold_fwd": (i32, [vp] * 9 + [i32, i32, vp, vp, vp, vp]),
     "onr_erb_fold_bwd": (i32, [vp] * 6 + [i32, i32] + [vp] * 10 + [vp]),
+    "onr_fold_workspace_bytes": (sz, [i32, i32, i32]),
+    "onr_fold_plan_create": (i32, [C.POINTER(vp), i32, i32, vp, i32]),
+    "onr_fold_plan_destroy": (None, [vp]),
+    "onr_fold_plan_fwd": (i32, [vp] + [vp] * 9 + [vp, vp, vp]),
+    "onr_fold_plan_bwd": (i32, [vp, vp, vp] + [vp] * 9 + [vp]),
+    "onr_tapmajor_permute": (i32, [vp, vp, i32, i32, i32, vp]),
+    "onr_pack_weights_t": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "onr_unpack_wgrad_t": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     "onr_pack_weights": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
     "onr_unpack_wgrad": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     "onr_conv_plan_create": (i32, [C.POINTER(vp), C.POINTER(ConvDesc)]),

@@ -52,6 +52,7 @@ constexpr int kMaxRing = 8;
 struct ConvParams {
     int H, W, B;
     int tiles_w, tiles_h, n_tiles, total_tiles;
+    int cluster, px_tiles, pair_tiles;   // CTAs per cluster (1 or 2), pixel tiles, work items per cluster
     int block_n, ms;
     int chunks, cpi, n64, cj, sign;   // chunks per tap, chunks per shuffle row i, 64-wide chunks per i, channels per i
     int n_total, acc_bufs, issuers;
@@ -95,11 +96,17 @@ __device__ __forceinline__ Chunk chunk_of(const ConvParams& p, int ch) {
 
 struct TileCoord {
     int b, h0, w0, n0;
+    bool skip;     // padding work item of an odd-sized CTA pair: runs the loads / MMAs of its neighbour, stores nothing
 };
-__device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile) {
+// Work item q of a cluster = (n tile, `cluster` horizontally adjacent pixel tiles); CTA `rank` takes pixel tile
+// (q / n_tiles) * cluster + rank.  Both CTAs of a pair therefore walk the SAME weight tiles in the same order, which is
+// what lets them share every weight tile through TMA multicast.
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int q, int rank) {
     TileCoord t;
-    const int nt = tile % p.n_tiles;
-    int mt = tile / p.n_tiles;
+    const int nt = q % p.n_tiles;
+    int mt = (q / p.n_tiles) * p.cluster + rank;
+    t.skip = mt >= p.px_tiles;
+    if (t.skip) mt = p.px_tiles - 1;
     const int tw = mt % p.tiles_w;
     mt /= p.tiles_w;
     const int th = mt % p.tiles_h;
@@ -127,13 +134,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int rank = p.cluster > 1 ? (int)cluster_ctarank() : 0;
+    const int q0 = blockIdx.x / p.cluster, qstep = gridDim.x / p.cluster;
+    const uint16_t mc_mask = (uint16_t)((1u << p.cluster) - 1u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxRing; ++s) {
             mbar_init(smem_u32(&bars->a_full[s]), 1);
             mbar_init(smem_u32(&bars->a_empty[s]), 1);
             mbar_init(smem_u32(&bars->b_full[s]), 1);
-            mbar_init(smem_u32(&bars->b_empty[s]), 1);
+            // a weight slot is refilled (by multicast, in every CTA of the cluster) once ALL CTAs have consumed it
+            mbar_init(smem_u32(&bars->b_empty[s]), p.cluster);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bars->tmem_full[b]), p.issuers);
@@ -158,6 +169,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();     // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -168,8 +180,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         //  with R2UR moves — measured 285 vs 195 cycles per MMA in csrc/mma_bench.cu)
         {
             uint32_t slot = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = tile_coord(p, tile);
+            for (int tile = q0; tile < p.pair_tiles; tile += qstep) {
+                const TileCoord t = tile_coord(p, tile, rank);
                 for (int ch = 0; ch < p.chunks; ++ch) {
                     const Chunk c = chunk_of(p, ch);
                     const CUtensorMap* map = c.width == 64 ? &tmA64 : &tmA32;
@@ -190,13 +202,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
     } else if (warp == kWarpProdB) {
         // ===================================================================== weight producer
         {
+            // cluster of 2: each CTA fetches HALF of every weight tile (block_n / 2 rows) and multicasts it into both
+            // CTAs, so a weight byte leaves L2 once per pair of pixel tiles (the kernel is bound by L2 -> SM operand
+            // traffic, profiles/r01_ncu_full_*_block4_v4.txt); the full barrier of each CTA counts both halves.
             uint32_t slot = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = tile_coord(p, tile);
+            const int half_rows = p.block_n / p.cluster;
+            for (int tile = q0; tile < p.pair_tiles; tile += qstep) {
+                const TileCoord t = tile_coord(p, tile, rank);
                 for (int ch = 0; ch < p.chunks; ++ch) {
                     const Chunk c = chunk_of(p, ch);
                     const CUtensorMap* map = c.width == 64 ? &tmB64 : &tmB32;
                     const uint32_t bytes = (uint32_t)p.block_n * c.width * 2;
+                    const uint32_t half_bytes = (uint32_t)half_rows * c.width * 2;
                     const int k0 = c.ii * p.cj + c.jc0;
                     for (int dwi = 0; dwi < 3; ++dwi) {
                         const int kw = 1 + (dwi - 1) * p.sign;
@@ -206,7 +223,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                             if (elect_one()) {
                                 const uint32_t full = smem_u32(&bars->b_full[slot]);
                                 mbar_expect_tx(full, bytes);
-                                tma_load_3d(b_ring + slot * p.b_bytes, map, full, k0, t.n0, kh * 3 + kw);
+                                if (p.cluster > 1)
+                                    tma_load_3d_mc(b_ring + slot * p.b_bytes + rank * half_bytes, map, full, k0,
+                                                   t.n0 + rank * half_rows, kh * 3 + kw, mc_mask);
+                                else
+                                    tma_load_3d(b_ring + slot * p.b_bytes, map, full, k0, t.n0, kh * 3 + kw);
                             }
                             __syncwarp();
                             if (++slot == (uint32_t)p.nb) { slot = 0; phase ^= 1; }
@@ -234,7 +255,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         int it = 0;
         const bool prof = p.prof != nullptr && me == 0;
         long long t_start = prof ? clk() : 0, w_a = 0, w_b = 0, w_t = 0, t0 = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = q0; tile < p.pair_tiles; tile += qstep, ++it) {
             const int buf = it % p.acc_bufs;
             const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
             if (prof) t0 = clk();
@@ -297,7 +318,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                             }
                             if (p.issuers > 1 && !early) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));
 #pragma unroll
-                            for (int dhi = 0; dhi < 3; ++dhi) umma_commit(b_bar[dhi]);
+                            for (int dhi = 0; dhi < 3; ++dhi) {
+                                if (p.cluster > 1) umma_commit_mc(b_bar[dhi], mc_mask);   // frees the slot in both CTAs
+                                else umma_commit(b_bar[dhi]);
+                            }
                             umma_commit(smem_u32(&bars->a_empty[aslot]));
                         }
                         __syncwarp();
@@ -329,8 +353,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         int it = 0;
         const bool prof = p.prof != nullptr && store_thread;
         long long e_full = 0, e_store = 0, e_busy = 0, t0 = 0, t1 = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const TileCoord t = tile_coord(p, tile);
+        for (int tile = q0; tile < p.pair_tiles; tile += qstep, ++it) {
+            const TileCoord t = tile_coord(p, tile, rank);
             const int buf = it % p.acc_bufs;
             const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
             if (prof) t0 = clk();
@@ -340,7 +364,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
             const int ngroups = (p.block_n + 63) / 64;
             for (int ms = 0; ms < p.ms; ++ms) {
                 const int hs0 = t.h0 + ms * kSubH;
-                if (hs0 >= p.H) break;      // sub-tile entirely below the image (uniform across the CTA)
+                if (hs0 >= p.H || t.skip) break;      // sub-tile entirely below the image / padding work item
                 for (int g = 0; g < ngroups; ++g) {
                     const int n_g = t.n0 + g * 64;              // first output channel of the group
                     if (n_g >= p.n_total) break;
@@ -461,6 +485,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         }
     }
 
+    // the peer may still multicast weight tiles into this CTA's ring / arrive on its barriers until it is done as well
+    if (p.cluster > 1) cluster_sync_all();
     tc_fence_before();
     __syncthreads();
     if (warp == kWarpMma) {
@@ -548,6 +574,14 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     p.tiles_w = ceil_div(d->W, kSubW);
     p.tiles_h = ceil_div(d->H, kSubH * ms);
     p.total_tiles = d->B * p.tiles_h * p.tiles_w * n_tiles;
+    p.px_tiles = d->B * p.tiles_h * p.tiles_w;
+    // CTA pairs (weight multicast) once the layer has at least two tiles per SM; ONR_CONV_CLUSTER=1|2 overrides
+    p.cluster = (p.total_tiles >= 2 * num_sms() && block_n % 32 == 0) ? 2 : 1;
+    if (const char* e = getenv("ONR_CONV_CLUSTER")) {
+        const int v = atoi(e);
+        if (v == 1 || (v == 2 && block_n % 32 == 0)) p.cluster = v;
+    }
+    p.pair_tiles = ceil_div(p.px_tiles, p.cluster) * n_tiles;
     const int k_tap = d->a_s * d->a_s * d->a_cp;
     p.cj = d->a_s * d->a_cp;                      // channels per shuffle row i of the A view
     p.n64 = p.cj / 64;
@@ -584,14 +618,17 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     p.na = na;
     p.nb = nb;
     pl->smem = 1024 + (size_t)na * p.a_bytes + (size_t)nb * p.b_bytes + 2 * kStageOutBytes + sizeof(SmemBarriers);
-    pl->grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    {
+        const int max_clusters = num_sms() / p.cluster;
+        pl->grid = (p.pair_tiles < max_clusters ? p.pair_tiles : max_clusters) * p.cluster;
+    }
     // 64-channel maps only exist when the channel extent allows them; otherwise they alias the 32-wide ones
     const int a64 = p.cj >= 64 ? 64 : 32, o64 = p.out_jc >= 64 ? 64 : 32, b64 = k_tap >= 64 ? 64 : 32;
     const void* outd = d->kind == ONR_CONV_FPROP_TRAIN ? d->out_d : d->out;
     int rc = make_act_tmap(&pl->tmA64, d->a, d->B, d->H, d->W, d->a_cp, d->a_s, kSubW, box_h, a64);
     if (!rc) rc = make_act_tmap(&pl->tmA32, d->a, d->B, d->H, d->W, d->a_cp, d->a_s, kSubW, box_h, 32);
-    if (!rc) rc = make_weight_tmap(&pl->tmB64, d->w, 9, d->n_rows, k_tap, block_n, b64);
-    if (!rc) rc = make_weight_tmap(&pl->tmB32, d->w, 9, d->n_rows, k_tap, block_n, 32);
+    if (!rc) rc = make_weight_tmap(&pl->tmB64, d->w, 9, d->n_rows, k_tap, block_n / p.cluster, b64);
+    if (!rc) rc = make_weight_tmap(&pl->tmB32, d->w, 9, d->n_rows, k_tap, block_n / p.cluster, 32);
     if (!rc) rc = make_act_tmap(&pl->tmY64, d->out, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, o64);
     if (!rc) rc = make_act_tmap(&pl->tmY32, d->out, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, 32);
     if (!rc) rc = make_act_tmap(&pl->tmD64, outd, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, o64);
@@ -621,8 +658,25 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
 int onr_conv_plan_run(const onr_conv_plan* pl, void* stream) {
     using namespace onr;
     ONR_REQUIRE(pl != nullptr, "null plan");
-    conv_igemm_kernel<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(
-        pl->tmA64, pl->tmA32, pl->tmB64, pl->tmB32, pl->tmY64, pl->tmY32, pl->tmD64, pl->tmD32, pl->p);
+    if (pl->p.cluster > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pl->grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = pl->smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pl->p.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ONR_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, pl->tmA64, pl->tmA32, pl->tmB64, pl->tmB32, pl->tmY64,
+                                    pl->tmY32, pl->tmD64, pl->tmD32, pl->p));
+    } else {
+        conv_igemm_kernel<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(
+            pl->tmA64, pl->tmA32, pl->tmB64, pl->tmB32, pl->tmY64, pl->tmY32, pl->tmD64, pl->tmD32, pl->p);
+    }
     ONR_LAUNCH_CHECK();
     return 0;
 }

@@ -73,6 +73,23 @@ int make_weight_tmap(CUtensorMap* map, const void* ptr, int taps, int rows, int 
     return 0;
 }
 
+int make_f32_2d_tmap(CUtensorMap* map, const void* ptr, int rows, int k, int pitch, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    ONR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    ONR_REQUIRE(pitch % 4 == 0 && pitch >= k && box_rows >= 1 && box_rows <= 256 && ((uintptr_t)ptr & 15) == 0,
+                "make_f32_2d_tmap: bad shape (rows %d k %d pitch %d box %d)", rows, k, pitch, box_rows);
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)4 * pitch};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ONR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32 2d) failed: %d (rows %d k %d pitch %d)", (int)r, rows, k,
+                pitch);
+    return 0;
+}
+
 }  // namespace onr
 
 extern "C" {

@@ -67,6 +67,10 @@ int make_act_tmap(CUtensorMap* map, const void* ptr, int B, int H, int W, int Cp
 // 3-D TMA view of packed weights [taps][rows][k] bf16; box = {inner, box_rows, 1}.
 int make_weight_tmap(CUtensorMap* map, const void* ptr, int taps, int rows, int k, int box_rows, int inner = 32);
 
+// 2-D TMA view of a K-major fp32 matrix [rows][k] with row pitch `pitch` floats (multiple of 4);
+// box = {32 floats = 128 B (SWIZZLE_128B), box_rows}.  Reads past `k` / `rows` are zero-filled.
+int make_f32_2d_tmap(CUtensorMap* map, const void* ptr, int rows, int k, int pitch, int box_rows);
+
 // ----------------------------------------------------------------------------- device helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -70,6 +70,41 @@ def _conv_plan(lib, **kw):
     return _Plan(h, lib.onr_conv_plan_destroy)
 
 
+class FoldPlan:
+    """Tensor-core ERB fold of one (Cin, Cout) block (csrc/fold_tc.cu): owns the workspace and the plan handle."""
+
+    def __init__(self, lib, cin, cout, train, device):
+        self.lib, self.cin, self.cout, self.train = lib, cin, cout, train
+        nbytes = lib.onr_fold_workspace_bytes(cin, cout, 1 if train else 0)
+        self.work = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        base = (self.work.data_ptr() + 1023) // 1024 * 1024
+        h = C.c_void_p()
+        check(lib.onr_fold_plan_create(C.byref(h), cin, cout, C.c_void_p(base), 1 if train else 0),
+              "onr_fold_plan_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.onr_fold_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+    def fwd(self, blk, Kt, bias, st):
+        b = blk
+        check(self.lib.onr_fold_plan_fwd(
+            self.handle, ptr(b.rbr_3x3_branch.weight), ptr(b.rbr_3x3_branch.bias),
+            ptr(b.rbr_1x3_branch.weight), ptr(b.rbr_1x3_branch.bias),
+            ptr(b.rbr_3x1_branch.weight), ptr(b.rbr_3x1_branch.bias),
+            ptr(b.rbr_1x1_3x3_1x1_branch_1x1_1.weight), ptr(b.rbr_1x1_3x3_1x1_branch_3x3.weight),
+            ptr(b.rbr_1x1_3x3_1x1_branch_1x1_2.weight), ptr(Kt), ptr(bias), st), "onr_fold_plan_fwd")
+
+    def bwd(self, dKt, dbias, g, st):
+        """g: the nine branch gradient tensors in the order (3x3 w, b, 1x3 w, b, 3x1 w, b, w1, w2, w3)."""
+        check(self.lib.onr_fold_plan_bwd(self.handle, ptr(dKt), ptr(dbias), *[ptr(t) for t in g], st),
+              "onr_fold_plan_bwd")
+
+
 def _wgrad_plan(lib, **kw):
     d = WgradDesc()
     for k, v in kw.items():
@@ -128,6 +163,10 @@ class NetExecutor:
 
         # ---- per block weights / gradient staging ------------------------------------------------
         self.K, self.bias, self.T, self.wf, self.wd, self.bias_p = [], [], [], [], [], []
+        # ERB fold on the tensor cores (3xTF32, csrc/fold_tc.cu) unless ONR_FOLD_SIMT=1 asks for round 1's fp32 SIMT
+        # contractions (kept for A/B timing and as a device-side cross-check)
+        self._fold_tc = os.environ.get("ONR_FOLD_SIMT", "0") != "1"
+        self.fold = []
         self.dKp, self.dbias_p, self.dK, self.dbias, self.dT, self.dKb = [], [], [], [], [], []
         # the wgrad kernels accumulate (red.global.add) into dKp / dbias_p: all of them live in one pool that a
         # single memset clears per step
@@ -140,9 +179,11 @@ class NetExecutor:
         self._wgrad_pool = zeros(total) if train else None
         for (g, blk), (off_k, off_b) in zip(zip(self.geoms, gen.layers), pool_off):
             erb = blk.is_erb_train()
+            # folded kernel: tap-major [Cout][9][Cin] on the tensor-core path, OIHW on the SIMT path (ONR_FOLD_SIMT=1)
             self.K.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
             self.bias.append(zeros(g.cout) if erb else None)
-            self.T.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
+            self.T.append(zeros(g.cout, g.cin, 3, 3) if (erb and not self._fold_tc) else None)
+            self.fold.append(FoldPlan(self.lib, g.cin, g.cout, train, dev) if (erb and self._fold_tc) else None)
             self.wf.append(zeros(9, g.npad, g.cpi, dtype=bf16))
             self.wd.append(zeros(9, g.cpi_rows, g.nk, dtype=bf16) if train else None)
             self.bias_p.append(zeros(g.npad))
@@ -156,7 +197,7 @@ class NetExecutor:
                 self.dKb.append(bucket)
                 self.dK.append(bucket[:nK].view(g.cout, g.cin, 3, 3))
                 self.dbias.append(bucket[nK:])
-                self.dT.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
+                self.dT.append(zeros(g.cout, g.cin, 3, 3) if (erb and not self._fold_tc) else None)
             else:
                 for lst in (self.dKp, self.dbias_p, self.dK, self.dbias, self.dT, self.dKb):
                     lst.append(None)
@@ -188,11 +229,14 @@ class NetExecutor:
 
     # ------------------------------------------------------------------------------------- helpers
     def _block_kernel(self, l):
-        """(K, bias) fp32 OIHW of block l, folding the ERB branches on the device when needed."""
+        """(K, bias, tap_major) of block l, folding the ERB branches on the device when needed."""
         blk = self.gen.layers[l]
         g = self.geoms[l]
         st = _lib.stream()
         if blk.is_erb_train():
+            if self._fold_tc:
+                self.fold[l].fwd(blk, self.K[l], self.bias[l], st)
+                return self.K[l], self.bias[l], True
             b = blk
             check(self.lib.onr_erb_fold_fwd(
                 ptr(b.rbr_3x3_branch.weight), ptr(b.rbr_3x3_branch.bias),
@@ -201,9 +245,9 @@ class NetExecutor:
                 ptr(b.rbr_1x1_3x3_1x1_branch_1x1_1.weight), ptr(b.rbr_1x1_3x3_1x1_branch_3x3.weight),
                 ptr(b.rbr_1x1_3x3_1x1_branch_1x1_2.weight),
                 g.cin, g.cout, ptr(self.K[l]), ptr(self.bias[l]), ptr(self.T[l]), st), "onr_erb_fold_fwd")
-            return self.K[l], self.bias[l]
+            return self.K[l], self.bias[l], False
         conv = blk.single_conv()
-        return conv.weight.detach(), conv.bias.detach()
+        return conv.weight.detach(), conv.bias.detach(), False
 
     def _side_streams(self):
         if getattr(self, "_side", None) is None:
@@ -260,11 +304,11 @@ class NetExecutor:
     def fold_pack_block(self, l):
         """Fold (ERB) + pack block l's kernel into the bf16 operand layouts on the current stream."""
         g, st = self.geoms[l], _lib.stream()
-        K, b = self._block_kernel(l)
-        check(self.lib.onr_pack_weights(
-            ptr(K), ptr(b), g.cin, g.cnew, g.s, g.npad, g.cpi_rows,
-            ptr(self.wf[l]), ptr(self.wd[l]) if self.train else None, ptr(self.bias_p[l]), st),
-            "onr_pack_weights")
+        K, b, tap_major = self._block_kernel(l)
+        pack = self.lib.onr_pack_weights_t if tap_major else self.lib.onr_pack_weights
+        check(pack(ptr(K), ptr(b), g.cin, g.cnew, g.s, g.npad, g.cpi_rows,
+                   ptr(self.wf[l]), ptr(self.wd[l]) if self.train else None, ptr(self.bias_p[l]), st),
+              "onr_pack_weights")
 
     # ------------------------------------------------------------------------------------- forward
     def forward(self, embed=None, t_norm=None, freqs=None, refresh=True, out=None):
@@ -393,8 +437,9 @@ class NetExecutor:
                 else:   # single-branch block: dK is the parameter gradient itself (grads are zero on entry)
                     name = f"layers.{l}." + blk.single_conv_name()
                     dK, db = grads[name + ".weight"], grads[name + ".bias"]
-                check(lib.onr_unpack_wgrad(ptr(self.dKp[l]), ptr(self.dbias_p[l]), g.cin, g.cnew, g.s,
-                                           ptr(dK), ptr(db), sst), "onr_unpack_wgrad")
+                unpack = lib.onr_unpack_wgrad_t if (blk.is_erb_train() and self._fold_tc) else lib.onr_unpack_wgrad
+                check(unpack(ptr(self.dKp[l]), ptr(self.dbias_p[l]), g.cin, g.cnew, g.s, ptr(dK), ptr(db), sst),
+                      "onr_unpack_wgrad")
                 if reduce is not None:
                     reduce(self.dKb[l] if blk.is_erb_train() else
                            self._flat_span(grads, [name + ".weight", name + ".bias"]))
@@ -438,7 +483,12 @@ class NetExecutor:
         """dK/dbias of ERB block l -> gradients of its nine branch tensors (fold backward)."""
         g, blk, st = self.geoms[l], self.gen.layers[l], _lib.stream()
         pfx = f"layers.{l}."
-        if True:
+        if self._fold_tc:
+            names = ("rbr_3x3_branch.weight", "rbr_3x3_branch.bias", "rbr_1x3_branch.weight", "rbr_1x3_branch.bias",
+                     "rbr_3x1_branch.weight", "rbr_3x1_branch.bias", "rbr_1x1_3x3_1x1_branch_1x1_1.weight",
+                     "rbr_1x1_3x3_1x1_branch_3x3.weight", "rbr_1x1_3x3_1x1_branch_1x1_2.weight")
+            self.fold[l].bwd(self.dK[l], self.dbias[l], [grads[pfx + n] for n in names], st)
+        else:
             b = blk
             check(self.lib.onr_erb_fold_bwd(
                 ptr(self.dK[l]), ptr(self.dbias[l]),

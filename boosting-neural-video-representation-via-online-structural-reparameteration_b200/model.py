@@ -40,36 +40,37 @@ def _fire_prune_hooks(conv):
 
 
 class _FoldFunction(torch.autograd.Function):
-    """ERB online fold (reference model.py:450-516) with its analytic backward."""
+    """ERB online fold (reference model.py:450-516) with its analytic backward, on the tensor-core
+    fold plan of the block (csrc/fold_tc.cu, 3xTF32 split precision: fp32-accurate)."""
 
     @staticmethod
-    def forward(ctx, w3x3, b3x3, w1x3, b1x3, w3x1, b3x1, w1, w2, w3):
+    def forward(ctx, blk, w3x3, b3x3, w1x3, b1x3, w3x1, b3x1, w1, w2, w3):
         lib = _lib.lib()
+        st = _lib.stream()
         cout, cin = w3x3.shape[0], w3x3.shape[1]
-        args = [t.detach().contiguous() for t in (w3x3, b3x3, w1x3, b1x3, w3x1, b3x1, w1, w2, w3)]
-        K = torch.empty_like(args[0])
-        bias = torch.empty_like(args[1])
-        T = torch.empty_like(args[0])
-        check(lib.onr_erb_fold_fwd(*[ptr(t) for t in args], cin, cout, ptr(K), ptr(bias), ptr(T),
-                                   _lib.stream()), "onr_erb_fold_fwd")
-        ctx.save_for_backward(args[6], args[7], args[8], T)
-        ctx.shapes = [t.shape for t in args]
+        plan = blk.fold_plan()
+        Kt = torch.empty(cout, 9, cin, dtype=torch.float32, device=w3x3.device)
+        bias = torch.empty(cout, dtype=torch.float32, device=w3x3.device)
+        plan.fwd(blk, Kt, bias, st)
+        K = torch.empty(cout, cin, 3, 3, dtype=torch.float32, device=w3x3.device)
+        check(lib.onr_tapmajor_permute(ptr(Kt), ptr(K), cin, cout, 1, st), "onr_tapmajor_permute")
+        ctx.plan = plan
+        ctx.shapes = [t.shape for t in (w3x3, b3x3, w1x3, b1x3, w3x1, b3x1, w1, w2, w3)]
         return K, bias
 
     @staticmethod
     def backward(ctx, dK, dbias):
         lib = _lib.lib()
-        w1, w2, w3, T = ctx.saved_tensors
-        cout, cin = T.shape[0], T.shape[1]
+        st = _lib.stream()
+        plan = ctx.plan
+        cout, cin = plan.cout, plan.cin
         dK = dK.contiguous()
         dbias = dbias.contiguous() if dbias is not None else torch.zeros(cout, device=dK.device)
+        dKt = torch.empty(cout, 9, cin, dtype=torch.float32, device=dK.device)
+        check(lib.onr_tapmajor_permute(ptr(dK), ptr(dKt), cin, cout, 0, st), "onr_tapmajor_permute")
         grads = [torch.zeros(s, dtype=torch.float32, device=dK.device) for s in ctx.shapes]
-        dT = torch.empty_like(T)
-        g3, gb3, g13, gb13, g31, gb31, gw1, gw2, gw3 = grads
-        check(lib.onr_erb_fold_bwd(ptr(dK), ptr(dbias), ptr(w1), ptr(w2), ptr(w3), ptr(T), cin, cout,
-                                   ptr(g3), ptr(gb3), ptr(g13), ptr(gb13), ptr(g31), ptr(gb31),
-                                   ptr(gw1), ptr(gw2), ptr(gw3), ptr(dT), _lib.stream()), "onr_erb_fold_bwd")
-        return tuple(grads)
+        plan.bwd(dKt, dbias, grads, st)
+        return (None,) + tuple(grads)
 
 
 class _BlockFunction(torch.autograd.Function):
@@ -174,6 +175,26 @@ class NeRVBlock(nn.Module):
     def is_erb_train(self):
         return (not self.deploy) and self.branch_type == "ERB" and hasattr(self, "rbr_3x3_branch")
 
+    def fold_plan(self):
+        """Tensor-core fold plan of this block (created on first use; holds the fold's workspace on the device)."""
+        dev = self.rbr_3x3_branch.weight.device
+        plan = self.__dict__.get("_fold_plan_obj")
+        if plan is None or plan.work.device != dev:
+            from .engine import FoldPlan
+            plan = FoldPlan(_lib.lib(), self.ngf, self.out_channels, True, dev)
+            self.__dict__["_fold_plan_obj"] = plan
+        return plan
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != "_fold_plan_obj":                    # plans hold raw device pointers: never copied
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
     def single_conv_name(self):
         return "rbr_reparam" if (self.deploy or not hasattr(self, "branch")) else "branch"
 
@@ -189,7 +210,7 @@ class NeRVBlock(nn.Module):
             raise AttributeError("get_equivalent_kernel_bias needs the ERB training branches")
         b = self
         return _FoldFunction.apply(
-            b.rbr_3x3_branch.weight, b.rbr_3x3_branch.bias, b.rbr_1x3_branch.weight, b.rbr_1x3_branch.bias,
+            self, b.rbr_3x3_branch.weight, b.rbr_3x3_branch.bias, b.rbr_1x3_branch.weight, b.rbr_1x3_branch.bias,
             b.rbr_3x1_branch.weight, b.rbr_3x1_branch.bias, b.rbr_1x1_3x3_1x1_branch_1x1_1.weight,
             b.rbr_1x1_3x3_1x1_branch_3x3.weight, b.rbr_1x1_3x3_1x1_branch_1x1_2.weight)
 
@@ -208,6 +229,7 @@ class NeRVBlock(nn.Module):
         for name in _ERB_BRANCHES + ("branch",):
             if hasattr(self, name):
                 self.__delattr__(name)
+        self.__dict__.pop("_fold_plan_obj", None)
         self.deploy = True
 
     def forward(self, x):

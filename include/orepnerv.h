@@ -78,6 +78,31 @@ int onr_erb_fold_bwd(const float* dK, const float* dbias, const float* w1, const
                      float* g3x3, float* gb3x3, float* g1x3, float* gb1x3, float* g3x1, float* gb3x1,
                      float* gw1, float* gw2, float* gw3, float* dT, void* stream);
 
+/* Tensor-core fold (csrc/fold_tc.cu): the same arithmetic as onr_erb_fold_fwd / _bwd with the six contractions as
+ * tcgen05 GEMMs in 3xTF32 split precision (fp32-accurate, bit-reproducible).  The folded kernel and its gradient
+ * travel "tap-major": Kt[Cout][9][Cin] (= K[o][i][kh][kw] with the tap index ahead of the input channel), which is
+ * the operand order of the convolution kernels.  A plan owns the TMA descriptors of one (Cin, Cout) block and a
+ * caller-provided workspace of onr_fold_workspace_bytes() bytes (1024-byte aligned); train = 0 plans only fold. */
+typedef struct onr_fold_plan onr_fold_plan;
+size_t onr_fold_workspace_bytes(int Cin, int Cout, int train);
+int onr_fold_plan_create(onr_fold_plan** out, int Cin, int Cout, void* workspace, int train);
+void onr_fold_plan_destroy(onr_fold_plan* plan);
+int onr_fold_plan_fwd(onr_fold_plan* plan, const float* w3x3, const float* b3x3, const float* w1x3,
+                      const float* b1x3, const float* w3x1, const float* b3x1, const float* w1, const float* w2,
+                      const float* w3, float* Kt /*[Cout][9][Cin]*/, float* bias /*[Cout]*/, void* stream);
+/* dKt[Cout][9][Cin], dbias[Cout] -> the nine branch gradients (reference OIHW layouts), OVERWRITTEN: the fold is the
+ * only consumer of the branch tensors, so nothing else contributes to these gradients within a backward pass. */
+int onr_fold_plan_bwd(onr_fold_plan* plan, const float* dKt, const float* dbias,
+                      float* g3x3, float* gb3x3, float* g1x3, float* gb1x3, float* g3x1, float* gb3x1,
+                      float* gw1, float* gw2, float* gw3, void* stream);
+/* Kt[Cout][9][Cin] <-> K[Cout][Cin][3][3] (to_oihw != 0: tap-major -> reference layout). */
+int onr_tapmajor_permute(const float* src, float* dst, int Cin, int Cout, int to_oihw, void* stream);
+/* onr_pack_weights / onr_unpack_wgrad for tap-major kernels. */
+int onr_pack_weights_t(const float* Kt, const float* bias, int Cin, int Cnew, int s, int Npad, int Cpi_rows,
+                       void* wf_bf16, void* wd_bf16, float* bias_p, void* stream);
+int onr_unpack_wgrad_t(const float* dKp, const float* dbias_p, int Cin, int Cnew, int s,
+                       float* dKt, float* dbias, void* stream);
+
 /* Pack a folded (or vanilla / deploy) OIHW fp32 kernel into the two bf16 implicit-GEMM operand
  * layouts the convolution kernels consume.  n' = (i*s+j)*Cpo + c  for reference channel
  * o = c*s*s + i*s + j (nn.PixelShuffle order, model.py:310), Cpo = pad32(Cnew), Cpi = pad32(Cin):

@@ -45,8 +45,10 @@ def test_one_step_parity_full_size_vanilla(dev):
 
 def test_convergence_gate_s720(dev):
     """north_star gate 3: same frames, seed and frame order, fixed epoch count -> final PSNR within 0.1 dB of the
-    fp32 oracle (reference loop main_train.py:222-267 on a 12-frame 720p clip, 24 epochs)."""
-    res = U.convergence_run(dev, "S720", n_frames=12, epochs=24)
+    fp32 oracle (reference loop main_train.py:222-267 on a 12-frame 720p clip, 60 epochs: long enough for both runs to
+    get through the fit's phase transition, whose onset is chaotic — it moves by epochs between two runs of the fp32
+    oracle itself — and to settle on the cosine schedule's tail)."""
+    res = U.convergence_run(dev, "S720", n_frames=12, epochs=60)
     U.record("convergence", res)
     print({k: v for k, v in res.items() if not isinstance(v, list)})
     assert res["ours_train_psnr"][-1] > res["ours_train_psnr"][0] + 3.0          # it does fit the clip

@@ -72,7 +72,7 @@ def test_positional_encoding(dev, golden):
     assert (out.cpu() - m['pe_embed']).abs().max().item() <= 2e-6
 
 
-@pytest.mark.parametrize("cin,cout", [(4, 16), (26, 650), (96, 384)])
+@pytest.mark.parametrize("cin,cout", [(4, 16), (26, 650), (96, 384), (112, 2800), (26, 864)])
 def test_erb_fold_forward_backward(dev, cin, cout):
     from orepnerv.model import NeRVBlock
     torch.manual_seed(3)
@@ -85,16 +85,28 @@ def test_erb_fold_forward_backward(dev, cin, cout):
              'rbr_1x1_3x3_1x1_branch_3x3.weight', 'rbr_1x1_3x3_1x1_branch_1x1_2.weight']
     sd = {k: v.detach().cpu() for k, v in blk.state_dict().items()}
     ws = [sd[n] for n in names]
+    # the reference arithmetic in float64 is the ground truth of the fp32 gate (an fp32 CPU einsum over K = 9*Cout =
+    # 25 200 terms carries ~1e-5 of rounding error of its own)
+    ws = [w.double() for w in ws]
     K_ref, b_ref = O.erb_fold(*ws)
     assert rel_l2(K, K_ref) <= 1e-5 and rel_l2(b, b_ref) <= 1e-5
     g = torch.Generator().manual_seed(4)
     dK, db = torch.randn(K.shape, generator=g), torch.randn(b.shape, generator=g)
     (K * dK.to(dev)).sum().add((b * db.to(dev)).sum()).backward()
-    ref = O.erb_fold_backward(dK, db, ws[6], ws[7], ws[8])
+    ref = O.erb_fold_backward(dK.double(), db.double(), ws[6], ws[7], ws[8])
     order = ['w3x3', 'b3x3', 'w1x3', 'b1x3', 'w3x1', 'b3x1', 'w1', 'w2', 'w3']
     params = dict(blk.named_parameters())
     for n, o in zip(names, order):
         assert rel_l2(params[n].grad, ref[o]) <= 1e-5, n
+    # bit-reproducible: split-K partials are combined in a fixed order (replicas of a data-parallel run must not drift)
+    first = {n: params[n].grad.clone() for n in names}
+    for p_ in params.values():
+        p_.grad = None
+    K2, b2 = blk.get_equivalent_kernel_bias()
+    assert torch.equal(K2, K) and torch.equal(b2, b)
+    (K2 * dK.to(dev)).sum().add((b2 * db.to(dev)).sum()).backward()
+    for n in names:
+        assert torch.equal(params[n].grad, first[n]), n
 
 
 @pytest.mark.parametrize("cin,cnew,s,h,w", [(4, 4, 2, 6, 8), (26, 26, 5, 9, 16), (26, 96, 2, 13, 21), (96, 96, 3, 8, 16)])
