@@ -47,7 +47,7 @@ class WgradDesc(C.Structure):
     ]
 
 
-CONV_FPROP_TRAIN, CONV_FPROP_INFER, CONV_DGRAD = 0, 1, 2
+CONV_FPROP_TRAIN, CONV_FPROP_INFER, CONV_DGRAD, CONV_FPROP_Z = 0, 1, 2, 3
 
 _SIGNATURES = {
     "onr_abi_version": (i32, []),
@@ -86,6 +86,8 @@ _SIGNATURES = {
     "onr_nhwc_bf16_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "onr_head_fwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
     "onr_head_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp]),
+    "onr_head_fwd_z": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
+    "onr_head_bwd_z": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp]),
     "onr_head_bwd_dz": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp]),
     "onr_head_bwd_gw": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "onr_loss_workspace_bytes": (sz, [i32, i32, i32]),

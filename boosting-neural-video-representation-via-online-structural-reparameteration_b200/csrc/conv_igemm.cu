@@ -74,6 +74,10 @@ struct __align__(8) SmemBarriers {
     uint64_t b_full[kMaxRing], b_empty[kMaxRing];
     uint64_t tmem_full[2], tmem_empty[2], turn[2];
     uint32_t tmem_base;
+    // bias of the current tile's block_n channels (fprop), double-buffered over tiles: read from shared memory in the
+    // epilogue instead of 32 global loads per thread and iteration, whose latency eight epilogue warps cannot hide
+    // (role cycle counters: the fprop epilogue was busy 74 % of the kernel and set its pace)
+    alignas(16) float bias_s[2][kMaxBlockN];
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -358,6 +362,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
             const int buf = it % p.acc_bufs;
             const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
             if (prof) t0 = clk();
+            if (p.mode != ONR_CONV_DGRAD) {
+                // (a thread is never two tiles ahead of another — the per-iteration barriers below — so writing buffer
+                //  it & 1 cannot race with readers of the previous tile; the first barrier of the loop publishes it)
+                for (int i = threadIdx.x; i < p.block_n; i += kEpiThreads)
+                    bars->bias_s[it & 1][i] = t.n0 + i < p.n_total ? __ldg(p.bias + t.n0 + i) : 0.0f;
+            }
             mbar_wait(smem_u32(&bars->tmem_full[buf]), acc_phase);
             if (prof) { t1 = clk(); e_full += t1 - t0; }
             tc_fence_after();
@@ -422,19 +432,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                                              : "memory");
                             }
                         } else {
-                            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+                            const float4* bp = reinterpret_cast<const float4*>(&bars->bias_s[it & 1][col]);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float4 b0 = __ldg(bp + j * 2), b1 = __ldg(bp + j * 2 + 1);
+                                const float4 b0 = bp[j * 2], b1 = bp[j * 2 + 1];
                                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                                 float yv[8], dv[8];
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
                                     const float z = __uint_as_float(r[j * 8 + e]) + bb[e];
-                                    const float sg = fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
-                                    const float y = z * sg;
-                                    yv[e] = y;
-                                    dv[e] = fmaf(y, 1.0f - sg, sg);
+                                    if (p.mode == ONR_CONV_FPROP_Z) {      // pre-activation only (uniform branch)
+                                        yv[e] = z;
+                                        dv[e] = 0.0f;
+                                    } else {
+                                        const float sg = fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
+                                        const float y = z * sg;
+                                        yv[e] = y;
+                                        dv[e] = fmaf(y, 1.0f - sg, sg);
+                                    }
                                 }
                                 const uint32_t off = rbase + (((jofs + j) ^ sx) << 4);
                                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(ybuf + off),
@@ -534,7 +549,7 @@ int onr_conv_tile_n(int n_total, int* block_n, int* n_tiles) {
 int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     using namespace onr;
     ONR_REQUIRE(out && d, "null argument");
-    ONR_REQUIRE(d->kind >= 0 && d->kind <= 2, "bad conv kind %d", d->kind);
+    ONR_REQUIRE(d->kind >= 0 && d->kind <= 3, "bad conv kind %d", d->kind);
     ONR_REQUIRE(d->a_cp % 32 == 0 && d->out_cp % 32 == 0 && d->n_total % 32 == 0,
                 "channel counts must be multiples of 32 (a_cp %d out_cp %d n %d)", d->a_cp, d->out_cp,
                 d->n_total);
@@ -575,8 +590,10 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     p.tiles_h = ceil_div(d->H, kSubH * ms);
     p.total_tiles = d->B * p.tiles_h * p.tiles_w * n_tiles;
     p.px_tiles = d->B * p.tiles_h * p.tiles_w;
-    // CTA pairs (weight multicast) once the layer has at least two tiles per SM; ONR_CONV_CLUSTER=1|2 overrides
-    p.cluster = (p.total_tiles >= 2 * num_sms() && block_n % 32 == 0) ? 2 : 1;
+    // CTA pairs that share every weight tile by TMA multicast: ONR_CONV_CLUSTER=2
+    // (measured on B200: 0.169 vs 0.167 ms for block 4 — the kernel is not bound by L2 reads, each SM still ingests
+    //  every weight byte — so the pairing is off unless asked for)
+    p.cluster = 1;
     if (const char* e = getenv("ONR_CONV_CLUSTER")) {
         const int v = atoi(e);
         if (v == 1 || (v == 2 && block_n % 32 == 0)) p.cluster = v;

@@ -355,15 +355,11 @@ fold_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
                 const int gm_lo = mt * 128 + r0, gm_hi = min(mt * 128 + r0 + nrows, p.M);     // rows [gm_lo, gm_hi)
                 const int ncols = min(p.bn, p.N - n0);
                 for (int g = gm_lo / rd + ew; g * rd < gm_hi; g += kFtEpiWarps) {
-                    float* dst = q.hi + (long long)g * q.rs_hi + (long long)n0 * rd;
+                    const long long base = (long long)g * q.rs_hi + (long long)n0 * rd;
                     for (int v = lane; v < ncols * rd; v += 32) {
                         const int c = v / rd, rl = v - c * rd;
                         const int gm = g * rd + rl;
-                        if (gm >= gm_lo && gm < gm_hi) {
-                            const float val = tile[(gm - mt * 128) * part_pitch + c];
-                            if (q.accumulate) dst[v] += val;
-                            else dst[v] = val;
-                        }
+                        if (gm >= gm_lo && gm < gm_hi) ft_store(q, base + v, tile[(gm - mt * 128) * part_pitch + c]);
                     }
                 }
             } else {

@@ -306,6 +306,15 @@ head_bwd_fused_kernel(const float* __restrict__ gimg, const float* __restrict__ 
 // producer warp streams 128-pixel tiles of y, SiLU'(z) and the six gimg / img plane segments into a ring of shared
 // memory stages (cp.async.bulk + mbarrier transaction counts), 32 * chunks consumer threads reduce them.  The whole
 // ring is in flight while a tile is being consumed, which a register-fed loop at this register count cannot do.
+// SiLU and its derivative from the pre-activation, with the arithmetic of the convolution epilogue (conv_igemm.cu)
+__device__ __forceinline__ void silu_from_z(float z, float& y, float& d) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    const float sg = fmaf(0.5f, t, 0.5f);
+    y = z * sg;
+    d = fmaf(y, 1.0f - sg, sg);
+}
+
 constexpr int kHbPix = 128;          // pixels per stage
 constexpr int kHbMaxStages = 4;
 struct HeadStream {
@@ -313,12 +322,15 @@ struct HeadStream {
     uint32_t npix; int C, Cp; const float* Wh; int use_sigmoid;
     float* gWh; float* gbh; __nv_bfloat16* dz; int stages;
 };
+// kZ: `a.y` holds the pre-activation z and `a.dsilu` is unused — one activation stream instead of two.
+template <bool kZ>
 __global__ void __launch_bounds__(544, 1) head_bwd_stream_kernel(const HeadStream a) {
     extern __shared__ __align__(128) uint8_t hs_smem[];
     __shared__ float sg[3 * kHeadMaxC + 3];
     __shared__ __align__(8) uint64_t bars[2 * kHbMaxStages];
     const int chunks = a.Cp / 8;
-    const uint32_t act_bytes = kHbPix * a.Cp * 2, stage_bytes = 2 * act_bytes + 6 * kHbPix * 4;
+    constexpr uint32_t kActs = kZ ? 1u : 2u;
+    const uint32_t act_bytes = kHbPix * a.Cp * 2, stage_bytes = kActs * act_bytes + 6 * kHbPix * 4;
     const int S = a.stages;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kHbMaxStages]);
     const int n_cons_warps = chunks;           // 32 * chunks consumer threads
@@ -344,14 +356,14 @@ __global__ void __launch_bounds__(544, 1) head_bwd_stream_kernel(const HeadStrea
                 const uint32_t np = min((uint32_t)kHbPix, a.npix - pix0);
                 const uint32_t dst = smem_u32(hs_smem) + s * stage_bytes;
                 const uint32_t bar = full0 + 8 * s;
-                mbar_expect_tx(bar, 2 * np * a.Cp * 2 + 6 * np * 4);
+                mbar_expect_tx(bar, kActs * np * a.Cp * 2 + 6 * np * 4);
                 bulk_load_1d(dst, a.y + (size_t)pix0 * a.Cp, np * a.Cp * 2, bar);
-                bulk_load_1d(dst + act_bytes, a.dsilu + (size_t)pix0 * a.Cp, np * a.Cp * 2, bar);
+                if (!kZ) bulk_load_1d(dst + act_bytes, a.dsilu + (size_t)pix0 * a.Cp, np * a.Cp * 2, bar);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    bulk_load_1d(dst + 2 * act_bytes + k * kHbPix * 4, a.gimg + (size_t)k * a.npix + pix0, np * 4,
+                    bulk_load_1d(dst + kActs * act_bytes + k * kHbPix * 4, a.gimg + (size_t)k * a.npix + pix0, np * 4,
                                  bar);
-                    bulk_load_1d(dst + 2 * act_bytes + (3 + k) * kHbPix * 4, a.img + (size_t)k * a.npix + pix0,
+                    bulk_load_1d(dst + kActs * act_bytes + (3 + k) * kHbPix * 4, a.img + (size_t)k * a.npix + pix0,
                                  np * 4, bar);
                 }
             }
@@ -373,8 +385,8 @@ __global__ void __launch_bounds__(544, 1) head_bwd_stream_kernel(const HeadStrea
             mbar_wait(full0 + 8 * s, (it / S) & 1);
             const uint8_t* st = hs_smem + (size_t)s * stage_bytes;
             const uint4* sy = reinterpret_cast<const uint4*>(st);
-            const uint4* sd = reinterpret_cast<const uint4*>(st + act_bytes);
-            const float* sgi = reinterpret_cast<const float*>(st + 2 * act_bytes);
+            const uint4* sd = reinterpret_cast<const uint4*>(st + (kZ ? 0u : act_bytes));
+            const float* sgi = reinterpret_cast<const float*>(st + kActs * act_bytes);
             const uint32_t pix0 = t * kHbPix;
             const uint32_t np = min((uint32_t)kHbPix, a.npix - pix0);
 #pragma unroll
@@ -393,7 +405,12 @@ __global__ void __launch_bounds__(544, 1) head_bwd_stream_kernel(const HeadStrea
                 uint32_t out[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float y0 = bf16_lo(yu[e]), y1 = bf16_hi(yu[e]);
+                    float y0 = bf16_lo(yu[e]), y1 = bf16_hi(yu[e]);
+                    float s0 = bf16_lo(du[e]), s1 = bf16_hi(du[e]);
+                    if (kZ) {
+                        silu_from_z(y0, y0, s0);
+                        silu_from_z(y1, y1, s1);
+                    }
                     float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -402,7 +419,7 @@ __global__ void __launch_bounds__(544, 1) head_bwd_stream_kernel(const HeadStrea
                         d0 = fmaf(gp[k], w[k][2 * e], d0);
                         d1 = fmaf(gp[k], w[k][2 * e + 1], d1);
                     }
-                    out[e] = pack_bf16x2(d0 * bf16_lo(du[e]), d1 * bf16_hi(du[e]));
+                    out[e] = pack_bf16x2(d0 * s0, d1 * s1);
                 }
                 gb[0] += gp[0]; gb[1] += gp[1]; gb[2] += gp[2];
                 reinterpret_cast<uint4*>(a.dz)[(size_t)(pix0 + p) * chunks + ch] =
@@ -434,7 +451,7 @@ struct HeadFwdStream {
     float* img; int stages;
 };
 constexpr int kHfConsumers = 512;   // 16 warps x 8 pixels: one 128-pixel tile per pass
-template <int CPT>
+template <int CPT, bool kZ>
 __global__ void __launch_bounds__(32 + kHfConsumers, 1) head_fwd_stream_kernel(const HeadFwdStream a) {
     extern __shared__ __align__(128) uint8_t hs_smem[];
     __shared__ __align__(8) uint64_t bars[2 * 8];
@@ -491,7 +508,12 @@ __global__ void __launch_bounds__(32 + kHfConsumers, 1) head_fwd_stream_kernel(c
                 const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float lo = bf16_lo(u[e]), hi = bf16_hi(u[e]);
+                    float lo = bf16_lo(u[e]), hi = bf16_hi(u[e]);
+                    if (kZ) {
+                        float unused;
+                        silu_from_z(lo, lo, unused);
+                        silu_from_z(hi, hi, unused);
+                    }
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
                         acc[k] = fmaf(hi, w[i][k][2 * e + 1], fmaf(lo, w[i][k][2 * e], acc[k]));
@@ -520,22 +542,17 @@ static inline bool head_fits_u32(size_t npix, int chunks) { return npix * (size_
 
 }  // namespace onr
 
-extern "C" {
-
-int onr_head_fwd(const void* y, int B, int H, int W, int C, int Cp, const float* Wh, const float* bh,
-                 int use_sigmoid, float* img, void* stream) {
+template <bool kZ>
+static int head_fwd_stream_launch(const void* y, size_t npix, int C, int Cp, const float* Wh, const float* bh,
+                                  int use_sigmoid, float* img, void* stream) {
     using namespace onr;
-    ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
-    const size_t npix = (size_t)B * H * W;
     const int chunks = Cp / 8;
-    ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
-    static const bool no_stream = getenv("ONR_HEAD_STREAM") && atoi(getenv("ONR_HEAD_STREAM")) == 0;
-    if (B == 1 && !no_stream) {
+    {
         const size_t stage_bytes = (size_t)kHbPix * Cp * 2;
         int stages = (int)((160 * 1024) / stage_bytes);
         if (stages > 8) stages = 8;
-        auto kern = chunks == 4 ? head_fwd_stream_kernel<1> : chunks == 8 ? head_fwd_stream_kernel<2>
-                  : chunks == 12 ? head_fwd_stream_kernel<3> : head_fwd_stream_kernel<4>;
+        auto kern = chunks == 4 ? head_fwd_stream_kernel<1, kZ> : chunks == 8 ? head_fwd_stream_kernel<2, kZ>
+                  : chunks == 12 ? head_fwd_stream_kernel<3, kZ> : head_fwd_stream_kernel<4, kZ>;
         static bool attr_set[4] = {false, false, false, false};
         if (!attr_set[chunks / 4 - 1]) {
             ONR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -549,6 +566,53 @@ int onr_head_fwd(const void* y, int B, int H, int W, int C, int Cp, const float*
         ONR_LAUNCH_CHECK();
         return 0;
     }
+}
+
+template <bool kZ>
+static int head_bwd_stream_launch(const float* gimg, const float* img, const void* y, const void* dsilu, size_t npix,
+                                  int C, int Cp, const float* Wh, int use_sigmoid, float* gWh, float* gbh, void* dz,
+                                  void* stream) {
+    using namespace onr;
+    const int chunks = Cp / 8;
+    const size_t stage_bytes = (kZ ? 1 : 2) * (size_t)kHbPix * Cp * 2 + 6 * kHbPix * 4;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > kHbMaxStages) stages = kHbMaxStages;
+    ONR_REQUIRE(stages >= 2, "head: stage does not fit shared memory");
+    static bool attr_set = false;
+    if (!attr_set) {
+        ONR_CUDA(cudaFuncSetAttribute(head_bwd_stream_kernel<kZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+        attr_set = true;
+    }
+    HeadStream hs{gimg, img, reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dsilu),
+                  (uint32_t)npix, C, Cp, Wh, use_sigmoid, gWh, gbh, reinterpret_cast<__nv_bfloat16*>(dz), stages};
+    const int ntiles = (int)((npix + kHbPix - 1) / kHbPix);
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    head_bwd_stream_kernel<kZ><<<grid, 32 + 32 * chunks, stages * stage_bytes, (cudaStream_t)stream>>>(hs);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" {
+
+int onr_head_fwd_z(const void* z, int B, int H, int W, int C, int Cp, const float* Wh, const float* bh,
+                   int use_sigmoid, float* img, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
+    const size_t npix = (size_t)B * H * W;
+    ONR_REQUIRE(B == 1 && head_fits_u32(npix, Cp / 8), "head_fwd_z: single image only");
+    return head_fwd_stream_launch<true>(z, npix, C, Cp, Wh, bh, use_sigmoid, img, stream);
+}
+
+int onr_head_fwd(const void* y, int B, int H, int W, int C, int Cp, const float* Wh, const float* bh,
+                 int use_sigmoid, float* img, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
+    const size_t npix = (size_t)B * H * W;
+    const int chunks = Cp / 8;
+    ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
+    static const bool no_stream = getenv("ONR_HEAD_STREAM") && atoi(getenv("ONR_HEAD_STREAM")) == 0;
+    if (B == 1 && !no_stream) return head_fwd_stream_launch<false>(y, npix, C, Cp, Wh, bh, use_sigmoid, img, stream);
     const int threads = head_threads(chunks, 384);
     const int ppb = threads / chunks;
     ONR_REQUIRE(3 * ppb <= threads, "head: block too small to finish its pixels");
@@ -559,6 +623,15 @@ int onr_head_fwd(const void* y, int B, int H, int W, int C, int Cp, const float*
                                                     (uint32_t)(H * W), C, Cp, Wh, bh, use_sigmoid, img);
     ONR_LAUNCH_CHECK();
     return 0;
+}
+
+int onr_head_bwd_z(const float* gimg, const float* img, const void* z, int B, int H, int W, int C, int Cp,
+                   const float* Wh, int use_sigmoid, float* gWh, float* gbh, void* dz, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
+    const size_t npix = (size_t)B * H * W;
+    ONR_REQUIRE(B == 1 && npix % 4 == 0 && head_fits_u32(npix, Cp / 8), "head_bwd_z: single image with H*W % 4 == 0 only");
+    return head_bwd_stream_launch<true>(gimg, img, z, nullptr, npix, C, Cp, Wh, use_sigmoid, gWh, gbh, dz, stream);
 }
 
 int onr_head_bwd_dz(const float* gimg, const float* img, const void* dsilu, int B, int H, int W, int C, int Cp,
@@ -608,26 +681,8 @@ int onr_head_bwd(const float* gimg, const float* img, const void* y, const void*
     const int chunks = Cp / 8;
     ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
     static const bool no_stream = getenv("ONR_HEAD_STREAM") && atoi(getenv("ONR_HEAD_STREAM")) == 0;
-    if (B == 1 && npix % 4 == 0 && !no_stream) {
-        const size_t stage_bytes = 2 * (size_t)kHbPix * Cp * 2 + 6 * kHbPix * 4;
-        int stages = (int)((200 * 1024) / stage_bytes);
-        if (stages > kHbMaxStages) stages = kHbMaxStages;
-        ONR_REQUIRE(stages >= 2, "head: stage does not fit shared memory");
-        static bool attr_set = false;
-        if (!attr_set) {
-            ONR_CUDA(cudaFuncSetAttribute(head_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          200 * 1024));
-            attr_set = true;
-        }
-        HeadStream hs{gimg, img, reinterpret_cast<const __nv_bfloat16*>(y),
-                      reinterpret_cast<const __nv_bfloat16*>(dsilu), (uint32_t)npix, C, Cp, Wh, use_sigmoid,
-                      gWh, gbh, reinterpret_cast<__nv_bfloat16*>(dz), stages};
-        const int ntiles = (int)((npix + kHbPix - 1) / kHbPix);
-        const int grid = ntiles < num_sms() ? ntiles : num_sms();
-        head_bwd_stream_kernel<<<grid, 32 + 32 * chunks, stages * stage_bytes, (cudaStream_t)stream>>>(hs);
-        ONR_LAUNCH_CHECK();
-        return 0;
-    }
+    if (B == 1 && npix % 4 == 0 && !no_stream)
+        return head_bwd_stream_launch<false>(gimg, img, y, dsilu, npix, C, Cp, Wh, use_sigmoid, gWh, gbh, dz, stream);
     const int lanes = 384 / chunks;
     const int threads = lanes * chunks;
     int grid = (int)((npix + lanes - 1) / lanes);

@@ -76,7 +76,9 @@ class FoldPlan:
     def __init__(self, lib, cin, cout, train, device):
         self.lib, self.cin, self.cout, self.train = lib, cin, cout, train
         nbytes = lib.onr_fold_workspace_bytes(cin, cout, 1 if train else 0)
-        self.work = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        # filled with 0xFF (= NaN as fp32) once: a kernel that ever reads an operand element nobody wrote shows up as NaN
+        # instead of as a result that depends on what the allocator handed out
+        self.work = torch.full((nbytes + 1024,), 0xFF, dtype=torch.uint8, device=device)
         base = (self.work.data_ptr() + 1023) // 1024 * 1024
         h = C.c_void_p()
         check(lib.onr_fold_plan_create(C.byref(h), cin, cout, C.c_void_p(base), 1 if train else 0),
@@ -146,7 +148,13 @@ class NetExecutor:
         self.embed = zeros(B, self.E)
         self.pre1, self.h1, self.dh1 = zeros(B, self.hid), zeros(B, self.hid), zeros(B, self.hid)
 
-        # ---- activations: x[l] is the input of block l (x[L] = last block output) ----------------
+        # Training, single image: the LAST block stores only its bf16 pre-activation z (ONR_CONV_FPROP_Z) and the head
+        # kernels evaluate SiLU(z) / SiLU'(z) themselves — its output feeds nothing else, so the SiLU' map (177 MB at
+        # 720p) is never written and the block's epilogue, which set the pace of that kernel, shrinks to bias + convert.
+        self._head_fused = os.environ.get("ONR_HEAD_FUSED", "1") != "0"
+        self._last_z = (train and B == 1 and (self.H * self.W) % 4 == 0 and self._head_fused
+                        and os.environ.get("ONR_LAST_Z", "1") != "0" and os.environ.get("ONR_HEAD_STREAM", "1") != "0")
+        # ---- activations: x[l] is the input of block l (x[L] = last block output, or its pre-activation) ----
         self.x, self.d, self.dz = [], [], []
         for l in range(L + 1):
             if l == 0:
@@ -156,7 +164,8 @@ class NetExecutor:
                 hh, ww, cp = g.ho, g.wo, g.cpo
             self.x.append(zeros(B, hh, ww, cp, dtype=bf16))
             # x[0]/d[0] come from the stem kernel which always writes both
-            self.d.append(zeros(B, hh, ww, cp, dtype=bf16) if (train or l == 0) else None)
+            self.d.append(zeros(B, hh, ww, cp, dtype=bf16) if ((train and not (l == L and self._last_z)) or l == 0)
+                          else None)
             self.dz.append(zeros(B, hh, ww, cp, dtype=bf16) if train else None)
         self._img_static = zeros(B, 3, self.H, self.W)      # CUDA-graph paths always decode into this one
         self.img = self._img_static
@@ -206,12 +215,13 @@ class NetExecutor:
         lib = self.lib
         self.fprop, self.dgrad, self.wgrad = [], [], []
         for l, g in enumerate(self.geoms):
+            last_z = self._last_z and l == L - 1
+            kind = _lib.CONV_FPROP_Z if last_z else (_lib.CONV_FPROP_TRAIN if train else _lib.CONV_FPROP_INFER)
             self.fprop.append(_conv_plan(
-                lib, kind=_lib.CONV_FPROP_TRAIN if train else _lib.CONV_FPROP_INFER,
-                B=B, H=g.h, W=g.w, a=ptr(self.x[l]), a_cp=g.cpi, a_s=1,
+                lib, kind=kind, B=B, H=g.h, W=g.w, a=ptr(self.x[l]), a_cp=g.cpi, a_s=1,
                 w=ptr(self.wf[l]), n_rows=g.npad, n_total=g.nk,
                 out=ptr(self.x[l + 1]), out_cp=g.cpo, out_s=g.s,
-                out_d=ptr(self.d[l + 1]) if train else None, bias_p=ptr(self.bias_p[l]), dmul=None))
+                out_d=ptr(self.d[l + 1]) if (train and not last_z) else None, bias_p=ptr(self.bias_p[l]), dmul=None))
             if train:
                 self.dgrad.append(_conv_plan(
                     lib, kind=_lib.CONV_DGRAD, B=B, H=g.h, W=g.w,
@@ -224,7 +234,6 @@ class NetExecutor:
                     dz=ptr(self.dz[l + 1]), dz_cp=g.cpo, s=g.s,
                     dKp=ptr(self.dKp[l]), dbias_p=ptr(self.dbias_p[l])))
         self._wgrad_on_side = os.environ.get("ONR_WGRAD_SIDE", "1") != "0"
-        self._head_fused = os.environ.get("ONR_HEAD_FUSED", "1") != "0"
         self._fold_chain = int(os.environ.get("ONR_FOLD_CHAIN", "0"))
 
     # ------------------------------------------------------------------------------------- helpers
@@ -350,7 +359,8 @@ class NetExecutor:
                 main.wait_event(events[l])
             check(self.lib.onr_conv_plan_run(self.fprop[l].handle, st), "onr_conv_plan_run(fprop)")
         head = gen.head_conv()
-        check(self.lib.onr_head_fwd(
+        head_fwd = self.lib.onr_head_fwd_z if self._last_z else self.lib.onr_head_fwd
+        check(head_fwd(
             ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, self.geoms[-1].cpo,
             ptr(head.weight), ptr(head.bias), 1 if gen.sigmoid else 0, ptr(self.img), st), "onr_head_fwd")
         return self.img
@@ -385,7 +395,22 @@ class NetExecutor:
             self._wgrad_pool.zero_()
             pool_clear = torch.cuda.Event()
             pool_clear.record(hside)
-        if self._head_fused:
+        if self._last_z:
+            # the same single pass, reading only the pre-activation z of the last block
+            check(lib.onr_head_bwd_z(
+                ptr(gimg), ptr(self.img), ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, gL.cpo,
+                ptr(head.weight), 1 if gen.sigmoid else 0, ptr(grads[hname + ".weight"]), ptr(grads[hname + ".bias"]),
+                ptr(self.dz[self.L]), st), "onr_head_bwd_z")
+            if reduce is not None:
+                head_done = torch.cuda.Event()
+                head_done.record(main)
+                with torch.cuda.stream(hside):
+                    hside.wait_event(head_done)
+                    reduce(self._flat_span(grads, [hname + ".weight", hname + ".bias"]))
+                    ev = torch.cuda.Event()
+                    ev.record(hside)
+                    joins.append(ev)
+        elif self._head_fused:
             # one pass over the pixels: dz = (Wh^T g_pre) * SiLU' and the head weight/bias gradient reduction
             check(lib.onr_head_bwd(
                 ptr(gimg), ptr(self.img), ptr(self.x[self.L]), ptr(self.d[self.L]), self.B, self.H, self.W,

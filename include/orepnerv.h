@@ -122,7 +122,10 @@ int onr_unpack_wgrad(const float* dKp, const float* dbias_p, int Cin, int Cnew, 
  * GEMM fed by TMA.  A plan owns only TMA descriptors for fixed buffers; create once, run per step. */
 typedef struct onr_conv_plan onr_conv_plan;
 
-enum { ONR_CONV_FPROP_TRAIN = 0, ONR_CONV_FPROP_INFER = 1, ONR_CONV_DGRAD = 2 };
+/* ONR_CONV_FPROP_Z: the epilogue stores the bf16 PRE-activation z = conv + bias only (no SiLU, no SiLU' map): for the
+ * last block of a training model, whose output feeds nothing but the RGB head — onr_head_fwd_z / onr_head_bwd_z
+ * evaluate SiLU(z) and SiLU'(z) on the fly, which saves one 177 MB map per 720p frame and most of the epilogue. */
+enum { ONR_CONV_FPROP_TRAIN = 0, ONR_CONV_FPROP_INFER = 1, ONR_CONV_DGRAD = 2, ONR_CONV_FPROP_Z = 3 };
 
 typedef struct {
     int kind;        /* ONR_CONV_* */
@@ -189,6 +192,13 @@ int onr_head_fwd(const void* y_bf16, int B, int H, int W, int C, int Cp,
 int onr_head_bwd(const float* gimg, const float* img, const void* y_bf16, const void* dsilu_bf16,
                  int B, int H, int W, int C, int Cp, const float* Wh, int use_sigmoid,
                  float* gWh, float* gbh, void* dz_bf16, void* stream);
+
+/* The same head on the last block's bf16 PRE-activation z (written by an ONR_CONV_FPROP_Z plan): y = SiLU(z) and
+ * SiLU'(z) are evaluated inside the kernels.  Single image only (B == 1, H*W % 4 == 0: the bulk-copy streaming path). */
+int onr_head_fwd_z(const void* z_bf16, int B, int H, int W, int C, int Cp, const float* Wh, const float* bh,
+                   int use_sigmoid, float* img, void* stream);
+int onr_head_bwd_z(const float* gimg, const float* img, const void* z_bf16, int B, int H, int W, int C, int Cp,
+                   const float* Wh, int use_sigmoid, float* gWh, float* gbh, void* dz_bf16, void* stream);
 
 /* The two halves of onr_head_bwd as separate launches (dz is on the critical path of the backward; the weight /
  * bias gradient reduction is not and can run on another stream). */

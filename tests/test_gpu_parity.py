@@ -72,7 +72,7 @@ def test_positional_encoding(dev, golden):
     assert (out.cpu() - m['pe_embed']).abs().max().item() <= 2e-6
 
 
-@pytest.mark.parametrize("cin,cout", [(4, 16), (26, 650), (96, 384), (112, 2800), (26, 864)])
+@pytest.mark.parametrize("cin,cout", [(4, 16), (12, 32), (26, 650), (96, 384), (112, 2800), (26, 864)])
 def test_erb_fold_forward_backward(dev, cin, cout):
     from orepnerv.model import NeRVBlock
     torch.manual_seed(3)
@@ -559,6 +559,23 @@ def test_head_kernels_vs_torch(dev, B, H, W, C):
         assert rel_l2(gb, br.grad) <= 1e-4, fused
         assert rel_l2(dz[..., :C], dz_ref) <= 6e-3, fused          # dz is stored as bf16
         assert dz[..., C:].abs().max().item() == 0.0 if Cp > C else True
+    if B == 1 and (H * W) % 4 == 0:
+        # z mode (last block of a training model stores only its pre-activation): SiLU / SiLU' evaluated in the kernels
+        z_d = y_d                                            # reuse the same bf16 values as pre-activations
+        zf = z_d.float()[..., :C].requires_grad_(True)
+        Wz, bz = Wh.clone().requires_grad_(True), bh.clone().requires_grad_(True)
+        act = torch.nn.functional.silu(zf)
+        ref_z = (torch.tanh(torch.einsum('bhwc,kc->bkhw', act, Wz) + bz.view(1, 3, 1, 1)) + 1) * 0.5
+        img_z = torch.zeros(B, 3, H, W, device=dev)
+        check(lib.onr_head_fwd_z(ptr(z_d), B, H, W, C, Cp, ptr(Wh), ptr(bh), 0, ptr(img_z), st), "head_fwd_z")
+        assert (img_z - ref_z).abs().max().item() <= 2e-3       # tanh.approx SiLU
+        ref_z.backward(gimg)
+        gW, gb = torch.zeros(3, C, device=dev), torch.zeros(3, device=dev)
+        dz = torch.zeros(B, H, W, Cp, device=dev, dtype=torch.bfloat16)
+        check(lib.onr_head_bwd_z(ptr(gimg), ptr(img_z), ptr(z_d), B, H, W, C, Cp, ptr(Wh), 0, ptr(gW), ptr(gb), ptr(dz),
+                                 st), "head_bwd_z")
+        assert rel_l2(gW, Wz.grad) <= 5e-3 and rel_l2(gb, bz.grad) <= 5e-3
+        assert rel_l2(dz.float()[..., :C], zf.grad) <= 1e-2
 
 
 def test_fold_ahead_matches_default(dev, golden, monkeypatch):
