@@ -625,8 +625,7 @@ def run_ours(opts):
         # the step graph holds captured NCCL kernels: release it before the communicator goes away
         # (destroy_process_group otherwise blocks on the communicator the live graph still references)
         dist.barrier()
-        torch.cuda.synchronize()
-        fit.graph = None
+        fit.release_graph()
         del fit
         import gc
         gc.collect()

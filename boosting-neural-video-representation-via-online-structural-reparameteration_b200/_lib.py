@@ -58,6 +58,9 @@ _SIGNATURES = {
     "onr_pos_encoding": (i32, [vp, i32, vp, i32, vp, vp]),
     "onr_frame_u8_to_f32": (i32, [vp, sz, vp, vp]),
     "onr_stem_bwd": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "onr_stem_factor_floats": (sz, [i32, i32, i32, i32, i32]),
+    "onr_stem_bwd_factors": (i32, [vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "onr_stem_grads_from_factors": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     "onr_erb_fold_fwd": (i32, [vp] * 9 + [i32, i32, vp, vp, vp, vp]),
     "onr_erb_fold_bwd": (i32, [vp] * 6 + [i32, i32] + [vp] * 10 + [vp]),
     "onr_fold_workspace_bytes": (sz, [i32, i32, i32]),

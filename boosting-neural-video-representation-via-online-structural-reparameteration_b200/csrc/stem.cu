@@ -204,9 +204,149 @@ __global__ void stem_bwd_layer1_kernel(const float* __restrict__ dh1, const floa
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Data-parallel exchange of the stem gradients in FACTORED form.  For one frame gW2 = g (x) h1 is a rank-1 matrix
+// (7.7 MB at S720, 33 MB at L720): all-reducing it is by far the largest and — coming last in the backward — the only
+// fully exposed piece of the gradient exchange.  Instead every rank publishes its factors
+//     slot = [ g[n_out] | h1[hid] | dpre1[hid] | embed[E] ]          (fp32, ~21 KB at S720)
+// the slots are all-gathered (latency-bound), and every rank forms the SUMS over ranks itself, in rank order, so all
+// replicas obtain bit-identical gradients:  gW2 = sum_r g_r (x) h1_r,  gb2 = sum_r g_r,
+// gW1 = sum_r dpre1_r (x) embed_r,  gb1 = sum_r dpre1_r.
+__global__ void __launch_bounds__(128)
+stem_factors_local_kernel(const __nv_bfloat16* __restrict__ g0, const float* __restrict__ W2, int hid, int fc_dim,
+                          int fh, int fw, int Cp, float* __restrict__ slot_g, float* __restrict__ dh1) {
+    // dh1[j] += sum_o W2[o][j] g[o] over this block's kStemFastRows rows; also converts g to fp32 into the slot
+    const int n_out = fc_dim * fh * fw, HW = fh * fw;
+    const int o_begin = blockIdx.x * kStemFastRows;
+    float g[kStemFastRows];
+#pragma unroll
+    for (int r = 0; r < kStemFastRows; ++r) {
+        const int o = o_begin + r;
+        g[r] = 0.0f;
+        if (o < n_out) {
+            const int c = o / HW, hw = o - c * HW;
+            g[r] = __bfloat162float(g0[(size_t)hw * Cp + c]);
+        }
+    }
+    if (threadIdx.x < kStemFastRows && o_begin + threadIdx.x < n_out) slot_g[o_begin + threadIdx.x] = g[threadIdx.x];
+#pragma unroll
+    for (int u = 0; u < kStemFastU; ++u) {
+        const int j = (threadIdx.x + u * 128) * 4;
+        if (j >= hid) break;
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int r = 0; r < kStemFastRows; ++r) {
+            if (o_begin + r >= n_out) break;
+            const float4 w = __ldg(reinterpret_cast<const float4*>(W2 + (size_t)(o_begin + r) * hid + j));
+            acc.x = fmaf(w.x, g[r], acc.x); acc.y = fmaf(w.y, g[r], acc.y);
+            acc.z = fmaf(w.z, g[r], acc.z); acc.w = fmaf(w.w, g[r], acc.w);
+        }
+        atomicAdd(&dh1[j], acc.x); atomicAdd(&dh1[j + 1], acc.y);
+        atomicAdd(&dh1[j + 2], acc.z); atomicAdd(&dh1[j + 3], acc.w);
+    }
+}
+
+// slot tail: h1, dpre1 = dh1 * SiLU'(pre1), embed
+__global__ void stem_factors_tail_kernel(const float* __restrict__ h1, const float* __restrict__ dh1,
+                                         const float* __restrict__ pre1, const float* __restrict__ embed, int hid, int E,
+                                         float* __restrict__ slot_h1, float* __restrict__ slot_dpre1,
+                                         float* __restrict__ slot_embed) {
+    const int n = hid > E ? hid : E;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        if (j < hid) {
+            const float z = pre1[j];
+            const float sg = 1.0f / (1.0f + expf(-z));
+            slot_h1[j] = h1[j];
+            slot_dpre1[j] = dh1[j] * (sg + z * sg * (1.0f - sg));
+        }
+        if (j < E) slot_embed[j] = embed[j];
+    }
+}
+
+// gW2[o][j] = sum_r g_r[o] h1_r[j]  (j in float4 pieces), gb2[o] = sum_r g_r[o];  OVERWRITES
+__global__ void __launch_bounds__(256)
+stem_from_factors_w2_kernel(const float* __restrict__ slots, int K, size_t stride, int n_out, int hid,
+                            float* __restrict__ gW2, float* __restrict__ gb2) {
+    const int q4 = hid / 4;
+    const size_t total = (size_t)n_out * q4;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / q4), j = (int)(idx % q4) * 4;
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float gsum = 0.0f;
+        for (int r = 0; r < K; ++r) {
+            const float* sl = slots + (size_t)r * stride;
+            const float g = sl[o];
+            const float4 h = *reinterpret_cast<const float4*>(sl + n_out + j);
+            acc.x = fmaf(g, h.x, acc.x); acc.y = fmaf(g, h.y, acc.y);
+            acc.z = fmaf(g, h.z, acc.z); acc.w = fmaf(g, h.w, acc.w);
+            gsum += g;
+        }
+        *reinterpret_cast<float4*>(gW2 + (size_t)o * hid + j) = acc;
+        if (j == 0) gb2[o] = gsum;
+    }
+}
+
+// gW1[j][e] = sum_r dpre1_r[j] embed_r[e], gb1[j] = sum_r dpre1_r[j];  OVERWRITES
+__global__ void stem_from_factors_w1_kernel(const float* __restrict__ slots, int K, size_t stride, int n_out, int hid,
+                                            int E, float* __restrict__ gW1, float* __restrict__ gb1) {
+    const int total = hid * E;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx / E, e = idx % E;
+        float gw = 0.0f, gb = 0.0f;
+        for (int r = 0; r < K; ++r) {
+            const float* sl = slots + (size_t)r * stride;
+            const float dpre = sl[n_out + hid + j];
+            gw = fmaf(dpre, sl[n_out + 2 * hid + e], gw);
+            gb += dpre;
+        }
+        gW1[idx] = gw;
+        if (e == 0) gb1[j] = gb;
+    }
+}
+
 }  // namespace onr
 
 extern "C" {
+
+size_t onr_stem_factor_floats(int fc_dim, int fh, int fw, int hid, int emb_len) {
+    const size_t n = (size_t)fc_dim * fh * fw + 2 * (size_t)hid + emb_len;
+    return (n + 63) / 64 * 64;      // slots stay 256-byte aligned
+}
+
+int onr_stem_bwd_factors(const void* g0, const float* embed, int emb_len, const float* pre1, const float* h1, int hid,
+                         const float* W2, int fc_dim, int fh, int fw, int Cp, float* slot, float* scratch_dh1,
+                         void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(hid % 4 == 0 && hid <= 128 * 4 * kStemFastU, "stem factors: unsupported widths");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_out = fc_dim * fh * fw;
+    ONR_CUDA(cudaMemsetAsync(scratch_dh1, 0, (size_t)hid * sizeof(float), st));
+    stem_factors_local_kernel<<<ceil_div(n_out, kStemFastRows), 128, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(g0), W2, hid, fc_dim, fh, fw, Cp, slot, scratch_dh1);
+    ONR_LAUNCH_CHECK();
+    stem_factors_tail_kernel<<<ceil_div(hid > emb_len ? hid : emb_len, 256), 256, 0, st>>>(h1, scratch_dh1, pre1, embed, hid, emb_len,
+                                                                 slot + n_out, slot + n_out + hid, slot + n_out + 2 * hid);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
+
+int onr_stem_grads_from_factors(const float* slots, int K, int emb_len, int hid, int fc_dim, int fh, int fw,
+                                float* gW1, float* gb1, float* gW2, float* gb2, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(K >= 1 && hid % 4 == 0, "stem factors: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_out = fc_dim * fh * fw;
+    const size_t stride = onr_stem_factor_floats(fc_dim, fh, fw, hid, emb_len);
+    size_t blocks = ((size_t)n_out * (hid / 4) + 255) / 256;
+    if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
+    stem_from_factors_w2_kernel<<<(int)blocks, 256, 0, st>>>(slots, K, stride, n_out, hid, gW2, gb2);
+    ONR_LAUNCH_CHECK();
+    stem_from_factors_w1_kernel<<<ceil_div(hid * emb_len, 256), 256, 0, st>>>(slots, K, stride, n_out, hid, emb_len, gW1,
+                                                                             gb1);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
 
 int onr_pe_stem_fwd(const float* t_norm, int B, const float* freqs, int levels, const float* W1,
                     const float* b1, int hid, const float* W2, const float* b2, int fc_dim, int fh, int fw,

@@ -20,6 +20,30 @@ from .optim import FusedAdam
 from .utils import LOSS_TERMS, lr_multiplier
 
 
+class _Exchange:
+    """What the executor's backward calls for the data-parallel gradient exchange: `exchange(t)` all-reduces a bucket;
+    `all_gather_slots` / `stem_slots` serve the factored stem exchange (engine.NetExecutor.backward)."""
+
+    def __init__(self, world):
+        self.world = world          # (no reference to the fitter: a cycle would keep its CUDA graph alive past `del`)
+        self._slots = None
+        if os.environ.get("ONR_DP_STEM", "factors") != "factors":
+            self.all_gather_slots = None        # ONR_DP_STEM=allreduce: all-reduce the stem matrices (A/B timing)
+
+    def __call__(self, t):
+        dist.all_reduce(t)
+
+    def stem_slots(self, ex):
+        if self._slots is None:
+            gen = ex.gen
+            n = int(ex.lib.onr_stem_factor_floats(gen.fc_dim, gen.fc_h, gen.fc_w, ex.hid, ex.E))
+            self._slots = torch.zeros(self.world, n, dtype=torch.float32, device=ex.dev)
+        return self._slots, dist.get_rank(), self.world
+
+    def all_gather_slots(self, slots, rank):
+        dist.all_gather_into_tensor(slots, slots[rank])
+
+
 class FrameFitter:
     def __init__(self, model, pe, args, optimizer=None, world_size=1, steps_per_epoch=None, data_size=None,
                  use_graph=True, with_msssim=True):
@@ -80,6 +104,7 @@ class FrameFitter:
         self.exchange = os.environ.get("ONR_DP_EXCHANGE", "bucket")
         if self.exchange not in ("bucket", "flat"):
             raise ValueError("ONR_DP_EXCHANGE must be bucket or flat")
+        self._exchange = _Exchange(world_size) if world_size > 1 else None
         self.graph = None
         self.use_graph = use_graph and self.device_sched
         self.host_step = 0
@@ -96,6 +121,7 @@ class FrameFitter:
         """Gradient exchange of one bucket: NCCL all-reduce (sum) over NVLink on the current (side) stream; the
         average is applied as grad_scale = 1/world inside the fused Adam kernel."""
         dist.all_reduce(t)
+
 
     def _body_pre(self):
         """frame conversion, forward, loss + its gradient, backward -> local gradients in self.flat_grad"""
@@ -123,7 +149,7 @@ class FrameFitter:
                 ms_done = torch.cuda.Event()
                 ms_done.record(self._ms_stream)
         self.ex.backward(self.gimg, self.grads, block_hook=self._update_block if self.fold_ahead else None,
-                         reduce=self._reduce if (self.world > 1 and self.exchange == "bucket") else None)
+                         reduce=self._exchange if (self.world > 1 and self.exchange == "bucket") else None)
         if ms_done is not None:
             torch.cuda.current_stream().wait_event(ms_done)
 
@@ -149,6 +175,12 @@ class FrameFitter:
         if self.device_sched:
             self._tick()
         self.opt.step(device_schedule=self.device_sched)
+
+    def release_graph(self):
+        """Drops the captured step graph.  With world > 1 it holds captured NCCL kernels: release it (and synchronise)
+        before `dist.destroy_process_group()`, which otherwise blocks on the communicator the live graph references."""
+        torch.cuda.synchronize()
+        self.graph = None
 
     def refresh_weights(self):
         """(Re)folds and packs every block from the current parameters.  Needed before the first step and after

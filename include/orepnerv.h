@@ -61,6 +61,18 @@ int onr_stem_bwd(const void* g0_bf16, int B, const float* embed, int emb_len,
                  float* gW1, float* gb1, float* gW2, float* gb2,
                  float* scratch_dh1 /* [B,hid] */, void* stream);
 
+/* Data-parallel form of the stem backward (batch 1 per rank): the stem gradients of one frame are rank-1, so ranks
+ * exchange the FACTORS (onr_stem_factor_floats() fp32 per rank: g | h1 | dpre1 | embed) with an all-gather instead of
+ * all-reducing the 7.7 .. 33 MB matrices, and each rank forms the sums over the K gathered slots in rank order
+ * (bit-identical on every rank).  onr_stem_grads_from_factors OVERWRITES gW1, gb1, gW2, gb2 with the SUM over ranks. */
+size_t onr_stem_factor_floats(int fc_dim, int fh, int fw, int hid, int emb_len);
+int onr_stem_bwd_factors(const void* g0_bf16, const float* embed, int emb_len, const float* pre1, const float* h1,
+                         int hid, const float* W2, int fc_dim, int fh, int fw, int Cp,
+                         float* slot /* this rank's slot */, float* scratch_dh1 /* [hid] */, void* stream);
+int onr_stem_grads_from_factors(const float* slots /* [K][onr_stem_factor_floats()] */, int K, int emb_len, int hid,
+                                int fc_dim, int fh, int fw, float* gW1, float* gb1, float* gW2, float* gb2,
+                                void* stream);
+
 /* ------------------------------------------------------------------ A3: ERB online fold
  * model.py:450-516 (get_equivalent_kernel_bias, _fuse_1x3_3x1_branch, _fuse_1x1_3x3_1x1_branch).
  * Inputs are the nine branch tensors in the reference's OIHW layouts.  Outputs:

@@ -8,6 +8,7 @@ parameter movement matches the oracle's, (4) both exchange schemes (bucketed dK 
 summation order.  Prints one JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import sys
@@ -51,7 +52,9 @@ def main():
         dist.all_gather(flats, flat)
         results[scheme] = (torch.stack(gathered).cpu(), [f.cpu() for f in flats],
                            {k: v.detach().cpu().clone() for k, v in gen.state_dict().items()})
+        fit.release_graph()
         del fit, gen
+        gc.collect()
     if rank == 0:
         sd, state = {k: v.clone() for k, v in g['init_state'].items()}, {}
         embed = O.pos_encoding(g['pos'], 1.25, 40)

@@ -17,7 +17,7 @@ def test_frame_fitter_world2_matches_oracle_batch2():
     port = 29500 + os.getpid() % 2000
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dp_gpu_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("DP_RESULT ")][-1]
     rep = json.loads(line[len("DP_RESULT "):])
@@ -25,5 +25,5 @@ def test_frame_fitter_world2_matches_oracle_batch2():
     assert rep["ranks_bit_identical"] and rep["flat_ranks_bit_identical"]   # replicas must never drift apart
     assert rep["max_loss_err"] <= 3e-3
     assert rep["max_mse_rel_err"] <= 2e-2
-    assert rep["max_movement_rel_err"] <= 0.35
+    assert rep["max_movement_rel_err"] <= 0.1          # measured 0.023 - 0.027
     assert rep["bucket_vs_flat_rel"] <= 2e-3
