@@ -632,9 +632,14 @@ static void choose_tiles(int M, int N, int K, int* bn, int* n_tiles, int* m_tile
     *m_tiles = ceil_div(M, 128);
     *k_stages = ceil_div(K, kFtKBox);
     const int tiles = nt * *m_tiles;
-    // split K when the tile count leaves SMs idle: at least two pipeline stages per split
-    // (the splits of a tile form a thread-block cluster: a power of two, at most the portable cluster size 8)
+    // Split K only to bound the LENGTH of a CTA's K loop (~kFtSplitStages pipeline stages), never just to fill idle
+    // SMs: these GEMMs run on side streams beside the persistent convolution kernels, every CTA of theirs takes a
+    // whole SM away from those for its (latency-bound) lifetime, and the contention costs more than the fold gains
+    // (ONR_FOLD_SPLIT_STAGES overrides; the splits of a tile form a thread-block cluster: a power of two <= 8).
+    static const int split_stages = getenv("ONR_FOLD_SPLIT_STAGES") ? atoi(getenv("ONR_FOLD_SPLIT_STAGES")) : 16;
     int cap = num_sms() / tiles;
+    const int want = ceil_div(*k_stages, split_stages > 0 ? split_stages : 16);
+    if (cap > want) cap = want;
     if (cap > *k_stages / 2) cap = *k_stages / 2;
     int s = 1;
     while (s * 2 <= cap && s * 2 <= 8) s *= 2;
