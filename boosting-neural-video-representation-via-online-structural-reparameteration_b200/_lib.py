@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
         ("out_d", vp),
         ("bias_p", vp),
         ("dmul", vp),
+        ("head_w", vp), ("head_b", vp), ("head_c", i32), ("use_sigmoid", i32), ("img", vp),
     ]
 
 
@@ -47,7 +48,7 @@ class WgradDesc(C.Structure):
     ]
 
 
-CONV_FPROP_TRAIN, CONV_FPROP_INFER, CONV_DGRAD, CONV_FPROP_Z = 0, 1, 2, 3
+CONV_FPROP_TRAIN, CONV_FPROP_INFER, CONV_DGRAD, CONV_FPROP_Z, CONV_FPROP_HEAD = 0, 1, 2, 3, 4
 
 _SIGNATURES = {
     "onr_abi_version": (i32, []),
@@ -75,6 +76,7 @@ _SIGNATURES = {
     "onr_unpack_wgrad": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     "onr_conv_plan_create": (i32, [C.POINTER(vp), C.POINTER(ConvDesc)]),
     "onr_conv_plan_run": (i32, [vp, vp]),
+    "onr_conv_plan_set_head": (i32, [vp, vp, vp, vp]),
     "onr_conv_plan_destroy": (None, [vp]),
     "onr_conv_plan_info": (i32, [vp] + [C.POINTER(i32)] * 5),
     "onr_conv_plan_set_prof": (i32, [vp, vp, C.POINTER(i32)]),

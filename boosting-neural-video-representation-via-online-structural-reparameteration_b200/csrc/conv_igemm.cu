@@ -48,11 +48,18 @@ constexpr int kMaxBlockN = 256;
 constexpr int kMaxMS = 4;
 constexpr int kMaxDynSmem = 232448;                // 227 KB: per-block opt-in maximum on sm_100
 constexpr int kMaxRing = 8;
+// Work items (tiles) are handed out DYNAMICALLY: a persistent CTA takes work item blockIdx.x first and every further one
+// from a global atomic counter.  With the static round-robin assignment a CTA that starts late — because a side-stream
+// kernel (wgrad, the ERB fold GEMMs, MS-SSIM) still holds its SM — kept its full share of tiles and the whole kernel
+// waited for it; now it simply processes fewer.
+constexpr int kSchedRing = 4;
 
 struct ConvParams {
     int H, W, B;
     int tiles_w, tiles_h, n_tiles, total_tiles;
     int cluster, px_tiles, pair_tiles;   // CTAs per cluster (1 or 2), pixel tiles, work items per cluster
+    int dynamic;                         // work items after a CTA's first one come from a global atomic counter
+    int* sched;                          // [0] next work item - gridDim, [1] CTAs finished (both zero between launches)
     int block_n, ms;
     int chunks, cpi, n64, cj, sign;   // chunks per tap, chunks per shuffle row i, 64-wide chunks per i, channels per i
     int n_total, acc_bufs, issuers;
@@ -62,6 +69,11 @@ struct ConvParams {
     int out_jc;              // channels per shuffle row i of the output view (out_s * out_cp)
     const float* bias;
     const __nv_bfloat16* dmul;
+    // FPROP_HEAD: RGB head fused into the epilogue
+    const float* head_w;     // [3][head_c]
+    const float* head_b;     // [3]
+    float* img;              // fp32 NCHW [B][3][H*out_s][W*out_s]
+    int head_c, use_sigmoid, out_s;
     // optional per-CTA cycle counters (selftest "prof" mode): [cta][8] =
     // {total, mma wait A, mma wait B, mma wait tmem_empty, epi wait tmem_full, epi wait store, epi busy, tiles}
     long long* prof;
@@ -73,11 +85,19 @@ struct __align__(8) SmemBarriers {
     uint64_t a_full[kMaxRing], a_empty[kMaxRing];
     uint64_t b_full[kMaxRing], b_empty[kMaxRing];
     uint64_t tmem_full[2], tmem_empty[2], turn[2];
+    // work-item feed: the A-producer warp fetches work items and publishes them to the other roles through this ring
+    uint64_t sched_full[kSchedRing], sched_empty[kSchedRing];
+    int sched_tile[kSchedRing];
     uint32_t tmem_base;
     // bias of the current tile's block_n channels (fprop), double-buffered over tiles: read from shared memory in the
     // epilogue instead of 32 global loads per thread and iteration, whose latency eight epilogue warps cannot hide
     // (role cycle counters: the fprop epilogue was busy 74 % of the kernel and set its pace)
     alignas(16) float bias_s[2][kMaxBlockN];
+    // FPROP_HEAD: head weights of the tile's channels (zero in the channel padding), bias, and the per-row partial
+    // dot products of the two column halves
+    alignas(16) float head_w_s[3][kMaxBlockN];
+    float head_b_s[4];
+    float head_red[2][128][3];
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -121,6 +141,19 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int q, int 
     return t;
 }
 
+// Consumer side of the work-item feed (every role but the A producer): all lanes wait, lane 0 releases the slot.
+struct TileFeed {
+    uint32_t slot = 0, phase = 0;
+    __device__ __forceinline__ int next(SmemBarriers* bars) {
+        mbar_wait(smem_u32(&bars->sched_full[slot]), phase);
+        const int tile = *reinterpret_cast<volatile int*>(&bars->sched_tile[slot]);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(&bars->sched_empty[slot]));
+        if (++slot == kSchedRing) { slot = 0; phase ^= 1; }
+        return tile;
+    }
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmA32,
                   const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmB32,
@@ -149,6 +182,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
             mbar_init(smem_u32(&bars->b_full[s]), 1);
             // a weight slot is refilled (by multicast, in every CTA of the cluster) once ALL CTAs have consumed it
             mbar_init(smem_u32(&bars->b_empty[s]), p.cluster);
+        }
+        for (int s = 0; s < kSchedRing; ++s) {
+            mbar_init(smem_u32(&bars->sched_full[s]), 1);
+            // released by the weight producer, every issuer warp and every epilogue warp
+            mbar_init(smem_u32(&bars->sched_empty[s]), 1 + p.issuers + kEpiWarps);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bars->tmem_full[b]), p.issuers);
@@ -184,7 +222,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         //  with R2UR moves — measured 285 vs 195 cycles per MMA in csrc/mma_bench.cu)
         {
             uint32_t slot = 0, phase = 0;
-            for (int tile = q0; tile < p.pair_tiles; tile += qstep) {
+            uint32_t fslot = 0, fphase = 0;
+            for (int n = 0;; ++n) {
+                // fetch the next work item and publish it (the end marker too, so that every role terminates)
+                mbar_wait(smem_u32(&bars->sched_empty[fslot]), fphase ^ 1);
+                if (elect_one()) {
+                    int next = q0 + n * qstep;
+                    if (p.dynamic && n > 0) next = qstep + atomicAdd(p.sched, 1);
+                    bars->sched_tile[fslot] = next;
+                    mbar_arrive(smem_u32(&bars->sched_full[fslot]));
+                }
+                __syncwarp();
+                const int tile = *reinterpret_cast<volatile int*>(&bars->sched_tile[fslot]);
+                if (++fslot == kSchedRing) { fslot = 0; fphase ^= 1; }
+                if (tile >= p.pair_tiles) break;
                 const TileCoord t = tile_coord(p, tile, rank);
                 for (int ch = 0; ch < p.chunks; ++ch) {
                     const Chunk c = chunk_of(p, ch);
@@ -211,7 +262,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
             // traffic, profiles/r01_ncu_full_*_block4_v4.txt); the full barrier of each CTA counts both halves.
             uint32_t slot = 0, phase = 0;
             const int half_rows = p.block_n / p.cluster;
-            for (int tile = q0; tile < p.pair_tiles; tile += qstep) {
+            TileFeed feed;
+            for (int tile = feed.next(bars); tile < p.pair_tiles; tile = feed.next(bars)) {
                 const TileCoord t = tile_coord(p, tile, rank);
                 for (int ch = 0; ch < p.chunks; ++ch) {
                     const Chunk c = chunk_of(p, ch);
@@ -259,7 +311,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         int it = 0;
         const bool prof = p.prof != nullptr && me == 0;
         long long t_start = prof ? clk() : 0, w_a = 0, w_b = 0, w_t = 0, t0 = 0;
-        for (int tile = q0; tile < p.pair_tiles; tile += qstep, ++it) {
+        TileFeed feed;
+        for (int tile = feed.next(bars); tile < p.pair_tiles; tile = feed.next(bars), ++it) {
             const int buf = it % p.acc_bufs;
             const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
             if (prof) t0 = clk();
@@ -305,7 +358,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                             // overwrites the accumulator and must reach the tensor pipe first.
                             // Decode plans (FPROP_INFER) keep strict issue order instead: the accumulation order, hence
                             // every output bit, is then reproducible run to run (a decoder must be deterministic).
-                            const bool early = !first_group && p.mode != ONR_CONV_FPROP_INFER;
+                            const bool early = !first_group && p.mode != ONR_CONV_FPROP_INFER && p.mode != ONR_CONV_FPROP_HEAD;
                             if (p.issuers > 1 && early) mbar_arrive(smem_u32(&bars->turn[me ^ 1]));
 #pragma unroll
                             for (int dhi = 0; dhi < 3; ++dhi) {
@@ -353,11 +406,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         const int row = q * 32 + lane;      // accumulator row == pixel inside the 16 x 8 sub-tile
         const int hl = row >> 3, wl = row & 7;
         const bool store_thread = (ew == 0 && lane == 0);
+        if (p.mode == ONR_CONV_FPROP_HEAD) {
+            // block_n == out_cp: every tile holds all channels of one PixelShuffle sub-pixel, in channel order
+            for (int i = threadIdx.x; i < 3 * p.block_n; i += kEpiThreads) {
+                const int k = i / p.block_n, c = i - k * p.block_n;
+                bars->head_w_s[k][c] = c < p.head_c ? __ldg(p.head_w + k * p.head_c + c) : 0.0f;
+            }
+            if (threadIdx.x < 3) bars->head_b_s[threadIdx.x] = __ldg(p.head_b + threadIdx.x);
+            named_bar_sync(1, kEpiThreads);
+        }
         uint32_t iter_ctr = 0;
         int it = 0;
         const bool prof = p.prof != nullptr && store_thread;
         long long e_full = 0, e_store = 0, e_busy = 0, t0 = 0, t1 = 0;
-        for (int tile = q0; tile < p.pair_tiles; tile += qstep, ++it) {
+        TileFeed feed;
+        for (int tile = feed.next(bars); tile < p.pair_tiles; tile = feed.next(bars), ++it) {
             const TileCoord t = tile_coord(p, tile, rank);
             const int buf = it % p.acc_bufs;
             const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
@@ -375,6 +438,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
             for (int ms = 0; ms < p.ms; ++ms) {
                 const int hs0 = t.h0 + ms * kSubH;
                 if (hs0 >= p.H || t.skip) break;      // sub-tile entirely below the image / padding work item
+                if (p.mode == ONR_CONV_FPROP_HEAD) {
+                    // ---- fused RGB head: SiLU -> 1x1 conv C->3 -> bias -> (tanh+1)/2, straight from the accumulator
+                    float pk[3] = {0.0f, 0.0f, 0.0f};
+                    // the two warps of a lane quarter split the tile's columns evenly, in 16-column pieces:
+                    // half 0 takes [0, block_n/2), half 1 the rest (block_n is a multiple of 32)
+                    const int c_begin = half * (p.block_n / 2), c_end = c_begin + p.block_n / 2;
+                    for (int col = c_begin; col < c_end; col += 16) {
+                        uint32_t r[16];
+                        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.ms + ms) * p.block_n + col, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float z = __uint_as_float(r[e]) + bars->bias_s[it & 1][col + e];
+                            const float y = z * fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
+                            pk[0] = fmaf(y, bars->head_w_s[0][col + e], pk[0]);
+                            pk[1] = fmaf(y, bars->head_w_s[1][col + e], pk[1]);
+                            pk[2] = fmaf(y, bars->head_w_s[2][col + e], pk[2]);
+                        }
+                    }
+                    bars->head_red[half][row][0] = pk[0];
+                    bars->head_red[half][row][1] = pk[1];
+                    bars->head_red[half][row][2] = pk[2];
+                    named_bar_sync(1, kEpiThreads);
+                    if (half == 0) {
+                        const int h = hs0 + hl, w = t.w0 + wl;
+                        if (h < p.H && w < p.W) {
+                            // n tile index == sub-pixel (i, j) of the PixelShuffle
+                            const int nt = t.n0 / p.block_n, si = nt / p.out_s, sj = nt - si * p.out_s;
+                            const size_t Ho = (size_t)p.H * p.out_s, Wo = (size_t)p.W * p.out_s;
+                            const size_t px = ((size_t)h * p.out_s + si) * Wo + (size_t)w * p.out_s + sj;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const float v = bars->head_red[0][row][k] + bars->head_red[1][row][k] + bars->head_b_s[k];
+                                const float o = p.use_sigmoid ? 1.0f / (1.0f + __expf(-v)) : (tanhf(v) + 1.0f) * 0.5f;
+                                p.img[((size_t)t.b * 3 + k) * Ho * Wo + px] = o;
+                            }
+                        }
+                    }
+                    named_bar_sync(2, kEpiThreads);
+                    continue;
+                }
                 for (int g = 0; g < ngroups; ++g) {
                     const int n_g = t.n0 + g * 64;              // first output channel of the group
                     if (n_g >= p.n_total) break;
@@ -508,6 +612,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (p.dynamic && threadIdx.x == 0) {
+        // the last CTA to finish re-arms the counters for the next launch (no memset node per launch)
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 }  // namespace onr
@@ -518,6 +631,10 @@ struct onr_conv_plan {
     onr::ConvParams p;
     int grid;
     size_t smem;
+    int* sched = nullptr;      // two device counters of the dynamic work-item feed (owned by the plan)
+    ~onr_conv_plan() {
+        if (sched) cudaFree(sched);
+    }
 };
 
 extern "C" {
@@ -549,7 +666,7 @@ int onr_conv_tile_n(int n_total, int* block_n, int* n_tiles) {
 int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     using namespace onr;
     ONR_REQUIRE(out && d, "null argument");
-    ONR_REQUIRE(d->kind >= 0 && d->kind <= 3, "bad conv kind %d", d->kind);
+    ONR_REQUIRE(d->kind >= 0 && d->kind <= 4, "bad conv kind %d", d->kind);
     ONR_REQUIRE(d->a_cp % 32 == 0 && d->out_cp % 32 == 0 && d->n_total % 32 == 0,
                 "channel counts must be multiples of 32 (a_cp %d out_cp %d n %d)", d->a_cp, d->out_cp,
                 d->n_total);
@@ -557,6 +674,13 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     ONR_REQUIRE(d->B >= 1 && d->H >= 1 && d->W >= 1, "bad grid");
     int block_n = 0, n_tiles = 0;
     onr_conv_tile_n(d->n_total, &block_n, &n_tiles);
+    if (d->kind == ONR_CONV_FPROP_HEAD) {
+        // one N tile per PixelShuffle sub-pixel, so that an accumulator row holds every channel of one output pixel
+        ONR_REQUIRE(d->out_cp <= kMaxBlockN && d->head_w && d->head_b && d->img && d->head_c > 0 && d->head_c <= d->out_cp,
+                    "fused head needs out_cp <= %d and the head tensors", kMaxBlockN);
+        block_n = d->out_cp;
+        n_tiles = d->out_s * d->out_s;
+    }
     ONR_REQUIRE(d->n_rows >= block_n * n_tiles, "packed weights need %d rows, got %d", block_n * n_tiles,
                 d->n_rows);
     if (d->kind == ONR_CONV_DGRAD) ONR_REQUIRE(d->dmul != nullptr, "dgrad needs dmul");
@@ -599,6 +723,9 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
         if (v == 1 || (v == 2 && block_n % 32 == 0)) p.cluster = v;
     }
     p.pair_tiles = ceil_div(p.px_tiles, p.cluster) * n_tiles;
+    p.dynamic = 0;      // measured on B200: 1.193 (dynamic) vs 1.172 ms/step (static) - the static order keeps the L2 locality; knob only
+    if (const char* e = getenv("ONR_CONV_DYNAMIC")) p.dynamic = (atoi(e) != 0 && p.cluster == 1) ? 1 : 0;
+    p.sched = nullptr;
     const int k_tap = d->a_s * d->a_s * d->a_cp;
     p.cj = d->a_s * d->a_cp;                      // channels per shuffle row i of the A view
     p.n64 = p.cj / 64;
@@ -616,6 +743,8 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     p.out_jc = d->out_s * d->out_cp;
     p.bias = d->bias_p;
     p.dmul = reinterpret_cast<const __nv_bfloat16*>(d->dmul);
+    p.head_w = d->head_w; p.head_b = d->head_b; p.img = d->img;
+    p.head_c = d->head_c; p.use_sigmoid = d->use_sigmoid; p.out_s = d->out_s;
     p.prof = nullptr;
     const int box_h = kSubH * ms + 2;
     const int wmax = p.n64 > 0 ? 64 : 32;               // widest chunk this plan uses
@@ -641,13 +770,14 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
     }
     // 64-channel maps only exist when the channel extent allows them; otherwise they alias the 32-wide ones
     const int a64 = p.cj >= 64 ? 64 : 32, o64 = p.out_jc >= 64 ? 64 : 32, b64 = k_tap >= 64 ? 64 : 32;
-    const void* outd = d->kind == ONR_CONV_FPROP_TRAIN ? d->out_d : d->out;
+    const void* out_ptr = d->kind == ONR_CONV_FPROP_HEAD ? d->a : d->out;     // (fused head: no bf16 output; maps unused)
+    const void* outd = d->kind == ONR_CONV_FPROP_TRAIN ? d->out_d : out_ptr;
     int rc = make_act_tmap(&pl->tmA64, d->a, d->B, d->H, d->W, d->a_cp, d->a_s, kSubW, box_h, a64);
     if (!rc) rc = make_act_tmap(&pl->tmA32, d->a, d->B, d->H, d->W, d->a_cp, d->a_s, kSubW, box_h, 32);
     if (!rc) rc = make_weight_tmap(&pl->tmB64, d->w, 9, d->n_rows, k_tap, block_n / p.cluster, b64);
     if (!rc) rc = make_weight_tmap(&pl->tmB32, d->w, 9, d->n_rows, k_tap, block_n / p.cluster, 32);
-    if (!rc) rc = make_act_tmap(&pl->tmY64, d->out, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, o64);
-    if (!rc) rc = make_act_tmap(&pl->tmY32, d->out, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, 32);
+    if (!rc) rc = make_act_tmap(&pl->tmY64, out_ptr, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, o64);
+    if (!rc) rc = make_act_tmap(&pl->tmY32, out_ptr, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, 32);
     if (!rc) rc = make_act_tmap(&pl->tmD64, outd, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, o64);
     if (!rc) rc = make_act_tmap(&pl->tmD32, outd, d->B, d->H, d->W, d->out_cp, d->out_s, kSubW, kSubH, 32);
     if (rc) { delete pl; return rc; }
@@ -667,6 +797,16 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
         set_error("conv plan needs %zu bytes of shared memory", pl->smem);
         delete pl;
         return -1;
+    }
+    if (p.dynamic) {
+        cudaError_t e = cudaMalloc(&pl->sched, 2 * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(pl->sched, 0, 2 * sizeof(int));
+        if (e != cudaSuccess) {
+            set_error("conv plan: counter allocation failed: %s", cudaGetErrorString(e));
+            delete pl;
+            return (int)e;
+        }
+        p.sched = pl->sched;
     }
     *out = pl;
     return 0;
@@ -695,6 +835,14 @@ int onr_conv_plan_run(const onr_conv_plan* pl, void* stream) {
             pl->tmA64, pl->tmA32, pl->tmB64, pl->tmB32, pl->tmY64, pl->tmY32, pl->tmD64, pl->tmD32, pl->p);
     }
     ONR_LAUNCH_CHECK();
+    return 0;
+}
+
+int onr_conv_plan_set_head(onr_conv_plan* pl, float* img, const float* head_w, const float* head_b) {
+    ONR_REQUIRE(pl != nullptr && pl->p.mode == ONR_CONV_FPROP_HEAD && img && head_w && head_b, "set_head: not a fused-head plan");
+    pl->p.img = img;
+    pl->p.head_w = head_w;
+    pl->p.head_b = head_b;
     return 0;
 }
 

@@ -146,7 +146,7 @@ static int run_conv(const Shape& sh, int kind, int reps, bool check) {
     CK(cudaMemset(o1, 0x7f, out_elems * 2));
     CK(cudaMemset(d1, 0x7f, out_elems * 2));
 
-    onr_conv_desc d;
+    onr_conv_desc d = {};
     memset(&d, 0, sizeof(d));
     d.kind = kind;
     d.B = sh.B; d.H = sh.H; d.W = sh.W;

@@ -154,6 +154,13 @@ class NetExecutor:
         self._head_fused = os.environ.get("ONR_HEAD_FUSED", "1") != "0"
         self._last_z = (train and B == 1 and (self.H * self.W) % 4 == 0 and self._head_fused
                         and os.environ.get("ONR_LAST_Z", "1") != "0" and os.environ.get("ONR_HEAD_STREAM", "1") != "0")
+        # Decode with the RGB head fused into the last block's epilogue (ONR_CONV_FPROP_HEAD; ONR_DECODE_FUSED=1): the last
+        # activation (177 MB at 720p) is never written, only the image is.  Measured on B200 it is NOT faster — the fused
+        # kernel needs one 96-wide N tile per sub-pixel and takes 0.221 ms against 0.177 + 0.044 ms for the 128-wide
+        # convolution plus the streaming head kernel (2853 vs 2890 frames/s) — so it is an option that saves memory,
+        # not the default.
+        self._decode_fused = ((not train) and pad32(self.C_last) <= 256
+                              and os.environ.get("ONR_DECODE_FUSED", "0") == "1")
         # ---- activations: x[l] is the input of block l (x[L] = last block output, or its pre-activation) ----
         self.x, self.d, self.dz = [], [], []
         for l in range(L + 1):
@@ -162,7 +169,7 @@ class NetExecutor:
             else:
                 g = self.geoms[l - 1]
                 hh, ww, cp = g.ho, g.wo, g.cpo
-            self.x.append(zeros(B, hh, ww, cp, dtype=bf16))
+            self.x.append(None if (l == L and self._decode_fused) else zeros(B, hh, ww, cp, dtype=bf16))
             # x[0]/d[0] come from the stem kernel which always writes both
             self.d.append(zeros(B, hh, ww, cp, dtype=bf16) if ((train and not (l == L and self._last_z)) or l == 0)
                           else None)
@@ -217,11 +224,18 @@ class NetExecutor:
         for l, g in enumerate(self.geoms):
             last_z = self._last_z and l == L - 1
             kind = _lib.CONV_FPROP_Z if last_z else (_lib.CONV_FPROP_TRAIN if train else _lib.CONV_FPROP_INFER)
+            extra = {}
+            if self._decode_fused and l == L - 1:
+                head = gen.head_conv()
+                kind = _lib.CONV_FPROP_HEAD
+                extra = dict(head_w=ptr(head.weight), head_b=ptr(head.bias), head_c=self.C_last,
+                             use_sigmoid=1 if gen.sigmoid else 0, img=ptr(self.img))
             self.fprop.append(_conv_plan(
                 lib, kind=kind, B=B, H=g.h, W=g.w, a=ptr(self.x[l]), a_cp=g.cpi, a_s=1,
                 w=ptr(self.wf[l]), n_rows=g.npad, n_total=g.nk,
                 out=ptr(self.x[l + 1]), out_cp=g.cpo, out_s=g.s,
-                out_d=ptr(self.d[l + 1]) if (train and not last_z) else None, bias_p=ptr(self.bias_p[l]), dmul=None))
+                out_d=ptr(self.d[l + 1]) if (train and not last_z) else None, bias_p=ptr(self.bias_p[l]), dmul=None,
+                **extra))
             if train:
                 self.dgrad.append(_conv_plan(
                     lib, kind=_lib.CONV_DGRAD, B=B, H=g.h, W=g.w,
@@ -354,11 +368,16 @@ class NetExecutor:
             ptr(self.embed), ptr(self.pre1), ptr(self.h1), ptr(self.x[0]), ptr(self.d[0]), st),
             "onr_pe_stem_fwd")
         main = torch.cuda.current_stream()
+        head = gen.head_conv()
+        if self._decode_fused:
+            check(self.lib.onr_conv_plan_set_head(self.fprop[-1].handle, ptr(self.img), ptr(head.weight), ptr(head.bias)),
+                  "onr_conv_plan_set_head")
         for l in range(self.L):
             if events is not None:
                 main.wait_event(events[l])
             check(self.lib.onr_conv_plan_run(self.fprop[l].handle, st), "onr_conv_plan_run(fprop)")
-        head = gen.head_conv()
+        if self._decode_fused:
+            return self.img
         head_fwd = self.lib.onr_head_fwd_z if self._last_z else self.lib.onr_head_fwd
         check(head_fwd(
             ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, self.geoms[-1].cpo,

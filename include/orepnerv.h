@@ -136,8 +136,13 @@ typedef struct onr_conv_plan onr_conv_plan;
 
 /* ONR_CONV_FPROP_Z: the epilogue stores the bf16 PRE-activation z = conv + bias only (no SiLU, no SiLU' map): for the
  * last block of a training model, whose output feeds nothing but the RGB head — onr_head_fwd_z / onr_head_bwd_z
- * evaluate SiLU(z) and SiLU'(z) on the fly, which saves one 177 MB map per 720p frame and most of the epilogue. */
-enum { ONR_CONV_FPROP_TRAIN = 0, ONR_CONV_FPROP_INFER = 1, ONR_CONV_DGRAD = 2, ONR_CONV_FPROP_Z = 3 };
+ * evaluate SiLU(z) and SiLU'(z) on the fly, which saves one 177 MB map per 720p frame and most of the epilogue.
+ * ONR_CONV_FPROP_HEAD: decode of the LAST block with the RGB head (model.py:620-623) fused into the epilogue:
+ * SiLU, the 1x1 conv C -> 3, bias and (tanh+1)/2 (or sigmoid) are applied to the accumulator tile and only the fp32
+ * image is written — the block's 177 MB activation (720p) never exists.  Needs out_cp <= 256 (one N tile per
+ * PixelShuffle sub-pixel). */
+enum { ONR_CONV_FPROP_TRAIN = 0, ONR_CONV_FPROP_INFER = 1, ONR_CONV_DGRAD = 2, ONR_CONV_FPROP_Z = 3,
+       ONR_CONV_FPROP_HEAD = 4 };
 
 typedef struct {
     int kind;        /* ONR_CONV_* */
@@ -153,10 +158,16 @@ typedef struct {
     void* out_d;     /* FPROP_TRAIN: SiLU'(z) in the same layout as out */
     const float* bias_p;  /* FPROP_*: [n_total] in n' order */
     const void* dmul;     /* DGRAD: NHWC bf16 [B][H][W][n_total] multiplied into the result */
+    /* FPROP_HEAD only: head weight [3][head_c] and bias [3] (fp32, reference layout of head_layers.N), activation
+       flag, and the image fp32 NCHW [B][3][H*out_s][W*out_s] (re-bindable with onr_conv_plan_set_image) */
+    const float* head_w; const float* head_b; int head_c; int use_sigmoid; float* img;
 } onr_conv_desc;
 
 int onr_conv_plan_create(onr_conv_plan** plan, const onr_conv_desc* desc);
 int onr_conv_plan_run(const onr_conv_plan* plan, void* stream);
+/* FPROP_HEAD plans: bind the image buffer (a fresh tensor per decoded frame on the reference API) and the head tensors
+ * of the next runs. */
+int onr_conv_plan_set_head(onr_conv_plan* plan, float* img, const float* head_w, const float* head_b);
 void onr_conv_plan_destroy(onr_conv_plan* plan);
 /* Tiling a plan chose: N tile, number of N tiles, 128-pixel sub-tiles per CTA tile, A / weight ring depths. */
 int onr_conv_plan_info(const onr_conv_plan* plan, int* block_n, int* n_tiles, int* ms, int* na, int* nb);

@@ -620,3 +620,25 @@ def test_decode_sees_parameters_updated_by_the_fitter(dev, golden):
         fresh = copy.deepcopy(gen)(embed)[0]          # new executor, packs from the current parameters
     assert not torch.equal(after, before)
     assert torch.equal(after, fresh)
+
+
+@pytest.mark.parametrize("name", ["small_erb.pt", "tiny_vanilla.pt"])
+def test_decode_fused_head_matches_unfused(dev, golden, monkeypatch, name):
+    """Decode with the RGB head fused into the last block's epilogue (ONR_CONV_FPROP_HEAD, ONR_DECODE_FUSED=1) against the
+    unfused pair of kernels and against the oracle: same image up to the bf16 rounding of the last activation that the
+    fused path no longer performs."""
+    g = golden(name)
+    bt = "ERB" if "erb" in name else "NeRV_vanilla"
+    imgs = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("ONR_DECODE_FUSED", fused)
+        pe, gen = build(g['cfg'], bt, dev)
+        with torch.no_grad():
+            imgs[fused] = gen(pe(g['pos']))[0].clone()
+        ex = gen.executor(g['pos'].numel(), False)
+        assert ex._decode_fused == (fused == "1")
+        with torch.no_grad():
+            again = gen(pe(g['pos']))[0]
+        assert torch.equal(again, imgs[fused])                   # decode is deterministic
+    assert rel_l2(imgs["1"], imgs["0"]) <= 3e-3
+    assert rel_l2(imgs["1"], g['img']) <= 1e-2
