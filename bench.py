@@ -89,7 +89,7 @@ class ClockSampler:
     (An external `nvidia-smi -lms 100` poller next to the persistent tcgen05 kernels coincided with GPU-side hangs
     on this driver — see DESIGN.md section 6 — so nothing is spawned here.)"""
 
-    def __init__(self, gpu_index, period_s=0.02):
+    def __init__(self, gpu_index, period_s=0.005):
         self.gpu, self.period, self.rows, self.thread = gpu_index, period_s, [], None
         self._stop = threading.Event()
         self.mode = os.environ.get("ONR_BENCH_SAMPLER", "nvml")      # nvml | smi | off
@@ -759,7 +759,7 @@ def main():
     _arm_watchdog(int(os.environ.get("ONR_BENCH_WATCHDOG_S", "900")))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
     ap.add_argument("--config", default="c1", choices=sorted(WORKLOADS),
