@@ -572,15 +572,16 @@ def run_ours(opts):
             blk.switch_to_deploy()                     # ERB branches folded into one 3x3 conv per block
         dep.eval()
         with torch.no_grad():
-            embeds = [pe(t_all[i:i + 1]) for i in range(8)]
+            n_emb = min(8, n_frames)
+            embeds = [pe(t_all[i:i + 1]) for i in range(n_emb)]
             for k in range(5):
-                dep(embeds[k % 8])
+                dep(embeds[k % n_emb])
             torch.cuda.synchronize()
             d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             n_dec = max(opts.steps, 20)
             d0.record()
             for k in range(n_dec):
-                dep(embeds[k % 8])
+                dep(embeds[k % n_emb])
             d1.record()
             torch.cuda.synchronize()
         ms_dec = d0.elapsed_time(d1) / n_dec

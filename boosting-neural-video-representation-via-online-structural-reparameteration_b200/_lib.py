@@ -84,9 +84,6 @@ _SIGNATURES = {
     "onr_wgrad_plan_create": (i32, [C.POINTER(vp), C.POINTER(WgradDesc)]),
     "onr_wgrad_plan_run": (i32, [vp, vp]),
     "onr_wgrad_plan_destroy": (None, [vp]),
-    "onr_mma_bench": (i32, [i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
-    "onr_simt_conv": (i32, [C.POINTER(ConvDesc), vp]),
-    "onr_simt_wgrad": (i32, [C.POINTER(WgradDesc), vp]),
     "onr_nchw_to_nhwc_bf16": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "onr_nhwc_bf16_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "onr_head_fwd": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]),

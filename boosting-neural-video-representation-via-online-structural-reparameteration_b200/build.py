@@ -23,9 +23,11 @@ NVCC_FLAGS = [
 # the fold / Adam kernels must track the fp32 reference; fast intrinsics are used explicitly where safe.
 
 LIB_SOURCES = [s for s in [
-    "onr_api.cu", "conv_igemm.cu", "wgrad_igemm.cu", "conv_simt.cu", "fold.cu", "fold_tc.cu", "stem.cu", "head.cu",
-    "loss_ssim.cu", "adam.cu", "evalops.cu", "mma_bench.cu",
+    "onr_api.cu", "conv_igemm.cu", "wgrad_igemm.cu", "fold.cu", "fold_tc.cu", "stem.cu", "head.cu",
+    "loss_ssim.cu", "adam.cu", "evalops.cu", "layout.cu",
 ] if os.path.exists(os.path.join(CSRC, s))]
+# test infrastructure (SIMT cross-check kernels, MMA issue microbenchmark): part of the self-test binary only
+SELFTEST_SOURCES = ["selftest.cu", "conv_simt.cu", "mma_bench.cu"]
 
 
 def _nvcc():
@@ -84,8 +86,8 @@ def build_all(force=False, verbose=False):
             print(out)
     _run([nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                       "--cudart", "static"], verbose)
-    _run([nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "selftest.cu"), "-o", SELFTEST_PATH, "-L" + HERE,
-                                 "-lorepnerv", "-Xlinker", "-rpath=$ORIGIN"], verbose)
+    _run([nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SELFTEST_SOURCES] +
+         ["-o", SELFTEST_PATH, "-L" + HERE, "-lorepnerv", "-Xlinker", "-rpath=$ORIGIN"], verbose)
     with open(STAMP, "w") as f:
         f.write(digest)
     return LIB_PATH

@@ -4,6 +4,7 @@
 // commits after each group, waiting for the commit every `depth` groups (so up to `depth` groups are in flight).
 // Reports cycles per MMA.  Answers: what does the single-CTA tensor pipe sustain, and what does it depend on?
 #include "onr_common.cuh"
+#include "selftest_kernels.h"
 #include "onr_ptx.cuh"
 
 namespace onr {

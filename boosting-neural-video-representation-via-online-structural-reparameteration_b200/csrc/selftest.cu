@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/orepnerv.h"
+#include "selftest_kernels.h"
 
 #define CK(x)                                                                         \
     do {                                                                              \

@@ -191,15 +191,6 @@ int onr_wgrad_plan_create(onr_wgrad_plan** plan, const onr_wgrad_desc* desc);
 int onr_wgrad_plan_run(const onr_wgrad_plan* plan, void* stream);
 void onr_wgrad_plan_destroy(onr_wgrad_plan* plan);
 
-/* Plain SIMT versions of the three convolution passes on the same layouts.  Test infrastructure
- * for on-device cross-checks at sizes the CPU oracle cannot reach; not used by the product path. */
-int onr_simt_conv(const onr_conv_desc* desc, void* stream);
-int onr_simt_wgrad(const onr_wgrad_desc* desc, void* stream);
-
-/* Test infrastructure: tcgen05.mma issue-rate microbenchmark (cycles for iters*per_commit MMAs per CTA). */
-int onr_mma_bench(int N, int nacc, int per_commit, int iters, int depth, int layout, int a_stride,
-                  int uniform, long long* out_dev, int grid, void* stream);
-
 /* Layout converters at the module boundary (NeRVBlock.forward takes/returns NCHW fp32). */
 int onr_nchw_to_nhwc_bf16(const float* src, int B, int C, int H, int W, int Cp, void* dst, void* stream);
 int onr_nhwc_bf16_to_nchw(const void* src, int B, int C, int H, int W, int Cp, float* dst, void* stream);
