@@ -15,7 +15,7 @@ from .utils import PositionalEncoding
 
 
 def build_parser(eval_mode=False):
-    p = argparse.ArgumentParser(fromfile_prefix_chars="@")
+    p = argparse.ArgumentParser(fromfile_prefix_chars="@", epilog=SUPPORTED)
     # dataset parameters
     p.add_argument('--vid', default=[None], type=int, nargs='+', help='video id list for training')
     p.add_argument('--scale', type=int, default=1)
@@ -82,8 +82,55 @@ def build_parser(eval_mode=False):
     return p
 
 
+SUPPORTED = ("supported on the B200 hot path: --branch_type NeRV_vanilla|ERB, --act swish, --norm none, --single_res, "
+             "--num_blocks 1, --stem_dim_num <dim>_1, --conv_type conv, --loss_type L2|L1|SSIM|Fusion1..Fusion9, "
+             "--lr_type cosine|const|step, and block input widths (fc_hw_dim channels x expansion, then "
+             "max(width/reduction, lower_width)) of at most 128 channels; README recipe: --embed 1.25_40 "
+             "--stem_dim_num 512_1 --fc_hw_dim 9_16_26 --expansion 1 --reduction 2 --lower_width 96 --strides 5 2 2 2 2 "
+             "--single_res --act swish --loss Fusion6 --branch_type ERB")
+
+
+def validate_args(args):
+    """One clear error for every flag combination outside the hot path (the reference's own defaults — act gelu,
+    multi-resolution heads, fc dim 128 with expansion 8 — are among them), instead of a NotImplementedError or a plan
+    failure deep inside the first step."""
+    from .utils import LOSS_TERMS
+    bad = []
+    if args.branch_type not in ('NeRV_vanilla', 'ERB'):
+        bad.append(f'--branch_type {args.branch_type}')
+    if args.act != 'swish':
+        bad.append(f'--act {args.act}')
+    if args.norm != 'none':
+        bad.append(f'--norm {args.norm}')
+    if not args.single_res:
+        bad.append('multi-resolution heads (pass --single_res)')
+    if args.num_blocks != 1:
+        bad.append(f'--num_blocks {args.num_blocks}')
+    if args.conv_type != 'conv':
+        bad.append(f'--conv_type {args.conv_type}')
+    if args.loss_type not in LOSS_TERMS:
+        bad.append(f'--loss_type {args.loss_type}')
+    try:
+        if int(str(args.stem_dim_num).split('_')[1]) != 1:
+            bad.append(f'--stem_dim_num {args.stem_dim_num}')
+        width = int(str(args.fc_hw_dim).split('_')[2])
+        widths = []
+        for i, s in enumerate(args.strides):
+            widths.append(width)
+            width = int(width * args.expansion) if i == 0 else max(width // (1 if s == 1 else args.reduction),
+                                                                     args.lower_width)
+        if max(widths) > 128:
+            bad.append(f'block input width {max(widths)} > 128 channels (fc_hw_dim {args.fc_hw_dim}, expansion '
+                       f'{args.expansion})')
+    except (IndexError, ValueError):
+        bad.append(f'--stem_dim_num {args.stem_dim_num} / --fc_hw_dim {args.fc_hw_dim}')
+    if bad:
+        raise SystemExit('orepnerv: unsupported configuration: ' + '; '.join(bad) + '\n' + SUPPORTED)
+
+
 def finish_args(args):
     """Derived fields exactly like reference main_train.py:111-138."""
+    validate_args(args)
     args.warmup = int(args.warmup * args.epochs)
     if args.debug:
         args.eval_freq = 1
@@ -129,19 +176,26 @@ class FrameCache:
             frames = synthetic_clip(n, h, w, device=device)
         else:
             frames = self._load_dir(f'../data/{dataset.lower()}', vid_list).to(device)
+        # reference model.py:26-44: the normalised index is i / N over the WHOLE sorted listing, computed before the
+        # --vid selection (frames come back with their listing positions), and __len__ is N // frame_gap
+        positions, n_listing = getattr(self, '_positions', None), getattr(self, '_n_listing', None)
         n_all = frames.size(0)
-        idx_all = [float(i) / n_all for i in range(n_all)]                 # reference model.py:37
-        keep = [i for i in range(n_all) if i % frame_gap == 0]              # reference model.py:40-44
+        if positions is None:
+            positions, n_listing = list(range(n_all)), n_all
+        idx_all = [float(pos) / n_listing for pos in positions]            # reference model.py:37
+        keep = [i * frame_gap for i in range(n_all // frame_gap)]          # reference model.py:40-44, :57
         self.frames = frames[keep].contiguous()
         self.t = torch.tensor([idx_all[i] for i in keep], dtype=torch.float32, device=device)
 
-    @staticmethod
-    def _load_dir(main_dir, vid_list):
+    def _load_dir(self, main_dir, vid_list):
         import numpy as np
         from PIL import Image
         names = sorted(os.listdir(main_dir))
+        positions = list(range(len(names)))
         if vid_list and vid_list[0] is not None:
-            names = [n for i, n in enumerate(names) if i in set(vid_list)]
+            positions = [i for i in positions if i in set(vid_list)]
+        self._positions, self._n_listing = positions, len(names)
+        names = [names[i] for i in positions]
         out = []
         for n in names:
             img = np.asarray(Image.open(os.path.join(main_dir, n)).convert('RGB'))

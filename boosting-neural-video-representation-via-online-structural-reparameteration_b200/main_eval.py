@@ -37,11 +37,27 @@ def prunable_modules(model):
 
 
 def global_prune(model, amount):
-    """prune.global_unstructured(L1Unstructured, amount) with the k-th value found on the device."""
+    """prune.global_unstructured(L1Unstructured, amount) with the k-th value found on the device.  Exactly
+    k = round(amount * N) entries are masked, as `torch.topk` does in the reference (main_eval.py:587): everything
+    strictly below the k-th magnitude, plus as many of the entries EQUAL to it (ties: exact zeros, repeated quantised
+    values) as are needed to reach k, taken in flat-index order."""
     mods = prunable_modules(model)
-    thr, k = global_magnitude_threshold([m.weight.detach() for m in mods], float(amount))
-    for m in mods:
-        mask = (m.weight.detach().abs() > thr).to(m.weight.dtype) if thr is not None else torch.ones_like(m.weight)
+    ws = [m.weight.detach() for m in mods]
+    thr, k = global_magnitude_threshold(ws, float(amount))
+    if thr is None:
+        masks = [torch.ones_like(w) for w in ws]
+    else:
+        flat = torch.cat([w.abs().reshape(-1) for w in ws])
+        below = flat < thr
+        ties = flat == thr
+        need = k - int(below.sum())
+        pruned = below | (ties & (torch.cumsum(ties, 0) <= need))
+        keep = (~pruned).to(ws[0].dtype)
+        masks, off = [], 0
+        for w in ws:
+            masks.append(keep[off:off + w.numel()].view_as(w))
+            off += w.numel()
+    for m, mask in zip(mods, masks):
         prune.custom_from_mask(m, 'weight', mask)
     total = sum(m.weight_mask.numel() for m in mods)
     zeros = sum(int((m.weight_mask == 0).sum()) for m in mods)

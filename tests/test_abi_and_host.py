@@ -113,14 +113,22 @@ def test_lr_schedule_matches_golden(golden):
         assert adjust_lr(Opt(), epoch, it, 132, args) == lr_ref
 
 
-def test_shard_indices_cover_every_frame():
+def test_shard_indices_follow_drop_last_batches():
+    """K ranks x batch 1 == the reference DataLoader with -b K and drop_last=True (main_train.py:207-209): floor(N/K)
+    steps per epoch, disjoint frames, the N % K tail of the epoch's permutation skipped."""
     for n, k in [(132, 8), (132, 1), (600, 8), (7, 4)]:
         per_rank = [sharding.shard_indices(n, k, r, epoch=3) for r in range(k)]
         steps = sharding.steps_per_epoch(n, k)
+        assert steps == n // k
         assert all(len(p) == steps for p in per_rank)
         seen = [i for p in per_rank for i in p]
-        assert set(seen) == set(range(n)) and len(seen) == steps * k
+        assert len(set(seen)) == len(seen) == steps * k and set(seen) <= set(range(n))
+        perm = sharding.epoch_permutation(n, 3)
+        assert set(seen) == set(perm[:steps * k])
     assert sharding.shard_indices(10, 2, 0, 0, shuffle=False) == [0, 2, 4, 6, 8]
+    assert sharding.steps_per_epoch(132, 8) == 16
+    # fewer frames than ranks: every rank still gets one frame
+    assert [len(sharding.shard_indices(2, 4, r, 0)) for r in range(4)] == [1, 1, 1, 1]
 
 
 def test_flat_gradient_buffer_is_aligned_and_complete(golden):
