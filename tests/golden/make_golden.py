@@ -116,8 +116,38 @@ def misc():
     print('misc.pt written')
 
 
+def a13_prune_quant():
+    """SURVEY 8a-A13 known-answer test with the reference's own calls: deploy-state model ->
+    prune.global_unstructured(stem Linears + rbr_reparam convs, L1Unstructured, 0.2) (main_eval.py:572-587) ->
+    quantize_per_tensor over EVERY state-dict entry, weight_orig and weight_mask included (main_eval.py:660-669) ->
+    load_state_dict (:703) -> decode.  Stores the deploy state, the quantised state dict and the decoded image."""
+    import torch.nn.utils.prune as prune
+    g = torch.load(os.path.join(HERE, 'small_erb.pt'), weights_only=False)
+    pe, dep = build(SMALL, 'ERB', deploy=True)
+    dep.load_state_dict(g['deploy_state'])
+    mods = [dep.stem[0], dep.stem[2]] + [blk.rbr_reparam for blk in dep.layers]
+    prune.global_unstructured([(m, 'weight') for m in mods], pruning_method=prune.L1Unstructured, amount=0.2)
+    zeros = sum(int((m.weight_mask == 0).sum()) for m in mods)
+    total = sum(m.weight_mask.numel() for m in mods)
+    with torch.no_grad():
+        cur = dep.state_dict()
+        pruned_state = {k: v.clone() for k, v in cur.items()}
+        for k, v in cur.items():
+            large = v.dim() in {2, 4} and 'bias' not in k
+            _, new_v = ref_utils.quantize_per_tensor(v, 8, 0 if large else -1)
+            cur[k] = new_v.detach().type_as(v)
+        dep.load_state_dict(cur)
+        img = dep(pe(g['pos']))[0].detach().clone()
+    out = {'cfg': SMALL, 'pos': g['pos'], 'deploy_state': g['deploy_state'], 'mask_zeros': zeros, 'mask_total': total,
+           'pruned_state': pruned_state, 'quant_state': {k: v.clone() for k, v in cur.items()}, 'img': img}
+    torch.save(out, os.path.join(HERE, 'a13_prune_quant.pt'))
+    ones = {k: float((v == 1).float().mean()) for k, v in cur.items() if k.endswith('weight_mask')}
+    print('a13_prune_quant.pt: mask zeros', zeros, '/', total, '; fraction of ones in the quantised masks', ones)
+
+
 if __name__ == '__main__':
     case(TINY, 'ERB', 'tiny_erb.pt')
     case(TINY, 'NeRV_vanilla', 'tiny_vanilla.pt')
     case(SMALL, 'ERB', 'small_erb.pt')
     misc()
+    a13_prune_quant()

@@ -642,3 +642,46 @@ def test_decode_fused_head_matches_unfused(dev, golden, monkeypatch, name):
         assert torch.equal(again, imgs[fused])                   # decode is deterministic
     assert rel_l2(imgs["1"], imgs["0"]) <= 3e-3
     assert rel_l2(imgs["1"], g['img']) <= 1e-2
+
+
+def test_a13_prune_quant_against_reference_golden(dev, golden):
+    """SURVEY 8a-A13 known-answer test.  The golden file was produced by the UNMODIFIED reference
+    (tests/golden/make_golden.py:a13_prune_quant): deploy model -> prune.global_unstructured 0.2 -> quantize_per_tensor
+    over every state-dict entry (weight_orig AND weight_mask) -> load_state_dict -> decode.  Our eval driver stages
+    (main_eval.global_prune, prune_and_quantise) must give the same mask count, bit-identical quantised tensors — the
+    masks come back as all ones, i.e. the reference's quantisation undoes its pruning, a quirk kept on purpose — and
+    the same decoded image."""
+    from orepnerv import main_eval
+    g = golden("a13_prune_quant.pt")
+    pe, dep = build(g['cfg'], "ERB", dev, deploy=True)
+    dep.load_state_dict(g['deploy_state'])
+    args = argparse.Namespace(prune_ratio=0.2, quant_bit=8, quant_axis=0)
+    zeros, total = main_eval.global_prune(dep, 0.2)
+    assert (zeros, total) == (g['mask_zeros'], g['mask_total'])
+    for k, v in dep.state_dict().items():
+        assert torch.equal(v.cpu(), g['pruned_state'][k]), k            # same masks, same weight_orig
+    args.prune_ratio = 1.0                                               # already pruned: quantise only
+    main_eval.prune_and_quantise(dep, args, 2, (18, 24))
+    sd = dep.state_dict()
+    assert set(sd) == set(g['quant_state'])
+    for k, v in sd.items():
+        assert torch.equal(v.cpu(), g['quant_state'][k]), k
+        if k.endswith('weight_mask'):
+            assert bool((v == 1).all()), k                               # the quirk: pruning is undone
+    with torch.no_grad():
+        img = dep(pe(g['pos']))[0]
+    assert rel_l2(img, g['img']) <= 1e-2
+
+
+def test_global_prune_hits_exactly_k_under_ties(dev, golden):
+    """Coarsely quantised weights have many equal magnitudes: exactly round(amount * N) entries must be masked, as
+    torch.topk does in the reference (main_eval.py:587), not every entry tied with the threshold."""
+    from orepnerv import main_eval
+    g = golden("small_erb.pt")
+    pe, dep = build(g['cfg'], "ERB", dev, deploy=True)
+    dep.load_state_dict(g['deploy_state'])
+    with torch.no_grad():
+        for m in main_eval.prunable_modules(dep):
+            m.weight.copy_((m.weight * 20).round() / 20)                 # values k/20: heavy ties, many exact zeros
+    zeros, total = main_eval.global_prune(dep, 0.3)
+    assert zeros == int(round(0.3 * total))
