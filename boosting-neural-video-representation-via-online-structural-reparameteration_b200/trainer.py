@@ -29,6 +29,11 @@ class _Exchange:
         self._slots = None
         if os.environ.get("ONR_DP_STEM", "factors") != "factors":
             self.all_gather_slots = None        # ONR_DP_STEM=allreduce: all-reduce the stem matrices (A/B timing)
+        # The stem gather closes the backward on the main stream; on the default communicator it would queue behind
+        # the last blocks' bucket all-reduces (one NCCL stream per communicator, FIFO).  Its own communicator lets it
+        # run beside them (ONR_DP_GATHER_GROUP=0: share the default one).
+        self.gather_group = (dist.new_group() if (world > 1 and os.environ.get("ONR_DP_GATHER_GROUP", "1") != "0")
+                             else None)
 
     def __call__(self, t):
         dist.all_reduce(t)
@@ -41,7 +46,7 @@ class _Exchange:
         return self._slots, dist.get_rank(), self.world
 
     def all_gather_slots(self, slots, rank):
-        dist.all_gather_into_tensor(slots, slots[rank])
+        dist.all_gather_into_tensor(slots, slots[rank], group=self.gather_group)
 
 
 class FrameFitter:
@@ -91,10 +96,20 @@ class FrameFitter:
         # total work, and six Adam launches replace one), hence off by default.
         self.fold_ahead = (world_size == 1 and args.lr_type in ('cosine', 'const')
                            and os.environ.get("ONR_FOLD_AHEAD", "0") == "1")
+        # Early Adam (ONR_ADAM_EARLY, default blocks 2,3,4): the update of a late block runs on that block's side stream
+        # as soon as its gradients are final (after its all-reduce + fold backward), beside the rest of the backward,
+        # so the Adam launch at the end of the step — on the critical path — only covers the early blocks, stem and head.
+        # Needs the device-side schedule (the tick moves to the head of the step).
+        early = os.environ.get("ONR_ADAM_EARLY", "2,3,4")
+        self.adam_early = ([int(x) for x in early.split(",") if x.strip() != ""]
+                           if (args.lr_type in ('cosine', 'const') and not self.fold_ahead) else [])
         named = list(model.named_parameters())
         self._block_params = [[p for n, p in named if n.startswith(f"layers.{l}.")] for l in range(self.ex.L)]
         in_blocks = {id(p) for ps in self._block_params for p in ps}
         self._rest_params = [p for _, p in named if id(p) not in in_blocks]
+        self.adam_early = [l for l in self.adam_early if 0 <= l < self.ex.L]
+        early_ids = {id(p) for l in self.adam_early for p in self._block_params[l]}
+        self._late_params = [p for _, p in named if id(p) not in early_ids]
         self._weights_valid = False
         # Gradient exchange (world > 1).  "bucket" (default): per-block all-reduce of the folded-kernel gradients
         # dK|dbias (12.8 MB at S720 instead of the 30 MB of branch gradients) issued on the block's side stream as soon
@@ -127,7 +142,7 @@ class FrameFitter:
         """frame conversion, forward, loss + its gradient, backward -> local gradients in self.flat_grad"""
         lib, st = self.lib, _lib.stream()
         B, H, W = self.B, self.H, self.W
-        if self.fold_ahead:
+        if self.fold_ahead or self.adam_early:
             self._tick()        # the per-block Adam updates inside the backward need this step's lr / step count
         check(lib.onr_frame_u8_to_f32(ptr(self.frame_u8), self.frame_u8.numel(), ptr(self.target), st), "u8_to_f32")
         img = self.ex.forward(t_norm=self.t_norm, freqs=self.freqs, refresh=not self.fold_ahead)
@@ -148,7 +163,8 @@ class FrameFitter:
                                      ptr(self.loss_work), _lib.stream()), "onr_msssim")
                 ms_done = torch.cuda.Event()
                 ms_done.record(self._ms_stream)
-        self.ex.backward(self.gimg, self.grads, block_hook=self._update_block if self.fold_ahead else None,
+        hook = self._update_block if self.fold_ahead else (self._adam_block if self.adam_early else None)
+        self.ex.backward(self.gimg, self.grads, block_hook=hook,
                          reduce=self._exchange if (self.world > 1 and self.exchange == "bucket") else None)
         if ms_done is not None:
             torch.cuda.current_stream().wait_event(ms_done)
@@ -157,6 +173,11 @@ class FrameFitter:
         """backward hook (runs on block l's side stream): Adam on the block's tensors, then fold + pack for the next step"""
         self.opt.step_params(self._block_params[l])
         self.ex.fold_pack_block(l)
+
+    def _adam_block(self, l):
+        """backward hook (block l's side stream, its gradients final): early Adam for the late blocks"""
+        if l in self.adam_early:
+            self.opt.step_params(self._block_params[l])
 
     def _tick(self):
         lr_dev, step_dev = self.opt.device_scalars(self.dev)
@@ -170,6 +191,10 @@ class FrameFitter:
         the blocks (stem, head) are left to update here"""
         if self.fold_ahead:
             self.opt.step_params(self._rest_params)
+            self.opt._step_count_host += 1
+            return
+        if self.adam_early:
+            self.opt.step_params(self._late_params)
             self.opt._step_count_host += 1
             return
         if self.device_sched:
