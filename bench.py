@@ -247,6 +247,10 @@ def run_reference(opts):
     if rank != 0:
         return
     w = WORKLOAD
+    # bounded sample: a CPU step of this workload takes 0.2 - 2.5 s, so at most 30 timed steps (and 2 warm-up steps)
+    # whatever --steps / --warmup ask for — the whole arm then ends within about a minute
+    asked = (opts.steps, opts.warmup)
+    opts.steps, opts.warmup = min(opts.steps, 30), min(opts.warmup, 2)
     total, cores = cpu_steps(opts.steps, opts.warmup)
     fps = opts.steps / total
     what = ("forward-only decodes of one frame (single-branch model)" if w['kind'] == 'decode' else
@@ -256,7 +260,8 @@ def run_reference(opts):
         "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": 1000.0 * total / opts.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w['name'], "batch_per_gpu": 1, "note": "CPU arm: oracle port of the "
-                   "reference step (reference is Python/PyTorch and /root/reference does not travel to the GPU box)"},
+                   "reference step (reference is Python/PyTorch and /root/reference does not travel to the GPU box); "
+                   f"bounded sample: {opts.steps} timed steps after {opts.warmup} warm-up (asked for {asked[0]} / {asked[1]})"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{opts.steps} {what} at {w['H']}x{w['W']}"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -29,10 +29,11 @@ class _Exchange:
         self._slots = None
         if os.environ.get("ONR_DP_STEM", "factors") != "factors":
             self.all_gather_slots = None        # ONR_DP_STEM=allreduce: all-reduce the stem matrices (A/B timing)
-        # The stem gather closes the backward on the main stream; on the default communicator it would queue behind
-        # the last blocks' bucket all-reduces (one NCCL stream per communicator, FIFO).  Its own communicator lets it
-        # run beside them (ONR_DP_GATHER_GROUP=0: share the default one).
-        self.gather_group = (dist.new_group() if (world > 1 and os.environ.get("ONR_DP_GATHER_GROUP", "1") != "0")
+        # The stem gather closes the backward on the main stream; on the default communicator it queues behind the last
+        # blocks' bucket all-reduces (one NCCL stream per communicator, FIFO).  Its own communicator
+        # (ONR_DP_GATHER_GROUP=1) lets it run beside them — measured on 8 B200s: 6113 vs 6140 frames/s with the shared
+        # one, so the shared communicator stays the default.
+        self.gather_group = (dist.new_group() if (world > 1 and os.environ.get("ONR_DP_GATHER_GROUP", "0") == "1")
                              else None)
 
     def __call__(self, t):
