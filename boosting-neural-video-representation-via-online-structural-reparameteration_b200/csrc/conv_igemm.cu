@@ -58,6 +58,8 @@ struct ConvParams {
     int H, W, B;
     int tiles_w, tiles_h, n_tiles, total_tiles;
     int cluster, px_tiles, pair_tiles;   // CTAs per cluster (1 or 2), pixel tiles, work items per cluster
+    int ksplit;                          // DGRAD of a small layer: K-groups of a tile split over ksplit work items
+    float* kacc;                         // [B*H*W][n_total] fp32 partial sums of the split (zeroed per launch)
     int dynamic;                         // work items after a CTA's first one come from a global atomic counter
     int* sched;                          // [0] next work item - gridDim, [1] CTAs finished (both zero between launches)
     int block_n, ms;
@@ -120,6 +122,7 @@ __device__ __forceinline__ Chunk chunk_of(const ConvParams& p, int ch) {
 
 struct TileCoord {
     int b, h0, w0, n0;
+    int g0, g1;    // K-groups (chunk, dw) of the tile this work item covers: all of them unless the plan splits K
     bool skip;     // padding work item of an odd-sized CTA pair: runs the loads / MMAs of its neighbour, stores nothing
 };
 // Work item q of a cluster = (n tile, `cluster` horizontally adjacent pixel tiles); CTA `rank` takes pixel tile
@@ -127,6 +130,11 @@ struct TileCoord {
 // what lets them share every weight tile through TMA multicast.
 __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int q, int rank) {
     TileCoord t;
+    const int groups = p.chunks * 3;
+    const int part = q % p.ksplit;               // (ksplit > 1 only with cluster == 1)
+    q /= p.ksplit;
+    t.g0 = (int)((long long)part * groups / p.ksplit);
+    t.g1 = (int)((long long)(part + 1) * groups / p.ksplit);
     const int nt = q % p.n_tiles;
     int mt = (q / p.n_tiles) * p.cluster + rank;
     t.skip = mt >= p.px_tiles;
@@ -242,6 +250,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                     const CUtensorMap* map = c.width == 64 ? &tmA64 : &tmA32;
                     const uint32_t bytes = (uint32_t)(kSubH * p.ms + 2) * kSubW * c.width * 2;
                     for (int dwi = 0; dwi < 3; ++dwi) {
+                        const int g = ch * 3 + dwi;
+                        if (g < t.g0 || g >= t.g1) continue;
                         mbar_wait(smem_u32(&bars->a_empty[slot]), phase ^ 1);
                         if (elect_one()) {
                             const uint32_t full = smem_u32(&bars->a_full[slot]);
@@ -272,6 +282,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                     const uint32_t half_bytes = (uint32_t)half_rows * c.width * 2;
                     const int k0 = c.ii * p.cj + c.jc0;
                     for (int dwi = 0; dwi < 3; ++dwi) {
+                        const int g = ch * 3 + dwi;
+                        if (g < t.g0 || g >= t.g1) continue;
                         const int kw = 1 + (dwi - 1) * p.sign;
                         for (int dhi = 0; dhi < 3; ++dhi) {
                             const int kh = 1 + (dhi - 1) * p.sign;
@@ -320,13 +332,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
             if (prof) w_t += clk() - t0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * p.ms * p.block_n;
+            const TileCoord tc = tile_coord(p, tile, rank);
             bool first_group = true;
             for (int ch = 0; ch < p.chunks; ++ch) {
                 const Chunk c = chunk_of(p, ch);
                 const uint32_t row_b = c.width == 64 ? 1024u : 512u;   // bytes per image row of the box == SBO
                 const uint32_t lay = c.width == 64 ? SWZ_128B : SWZ_64B;
                 const int ksl = c.width / 16;
-                for (int dwi = 0; dwi < 3; ++dwi, ++gidx, first_group = false) {
+                for (int dwi = 0; dwi < 3; ++dwi) {
+                    if (ch * 3 + dwi < tc.g0 || ch * 3 + dwi >= tc.g1) continue;     // split K: not this work item's group
                     const bool mine = (gidx % (uint32_t)p.issuers) == (uint32_t)me;
                     uint32_t b_s[3], b_bar[3], b_full[3], b_par[3];
                     uint32_t bs = bslot, bp = bphase;
@@ -386,6 +400,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                     bslot = bs;
                     bphase = bp;
                     if (++aslot == (uint32_t)p.na) { aslot = 0; aphase ^= 1; }
+                    ++gidx;
+                    first_group = false;
                 }
             }
             if (elect_one()) umma_commit(smem_u32(&bars->tmem_full[buf]));   // one arrival per issuer
@@ -498,7 +514,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                     named_bar_sync(1, kEpiThreads);
                     const uint32_t ybuf = staging + sbuf * 2 * kStageOutBytes;
                     const uint32_t dbuf = ybuf + kStageOutBytes;
-                    if (valid) {
+                    if (valid && p.ksplit > 1) {
+                        // split K: add this work item's partial sums into the fp32 scratch; conv_split_finish_kernel
+                        // applies the epilogue once every part has landed
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.ms + ms) * p.block_n + col, r);
+                        tmem_ld_wait();
+                        const int h = hs0 + hl, w = t.w0 + wl;
+                        if (h < p.H && w < p.W) {
+                            float* dst = p.kacc + ((size_t)(t.b * p.H + h) * p.W + w) * p.n_total + n;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst + j * 4),
+                                             "f"(__uint_as_float(r[j * 4])), "f"(__uint_as_float(r[j * 4 + 1])),
+                                             "f"(__uint_as_float(r[j * 4 + 2])), "f"(__uint_as_float(r[j * 4 + 3]))
+                                             : "memory");
+                        }
+                    } else if (valid) {
                         uint32_t r[32];
                         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.ms + ms) * p.block_n + col, r);
                         tmem_ld_wait();
@@ -570,7 +602,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(2, kEpiThreads);
-                    if (store_thread) {
+                    if (store_thread && p.ksplit == 1) {
                         const bool train = p.mode == ONR_CONV_FPROP_TRAIN;
                         if (wide) {
                             tma_store_5d(&tmY64, ybuf, ojc, t.w0, oi, hs0, t.b);
@@ -623,6 +655,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_consta
     }
 }
 
+// Split-K dgrad, second half: out = bf16(partial sums x SiLU'(z) of the producer), NHWC with out_s == 1.
+__global__ void conv_split_finish_kernel(const float* __restrict__ acc, const __nv_bfloat16* __restrict__ dmul,
+                                         __nv_bfloat16* __restrict__ out, size_t n) {
+    for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 2; i < n;
+         i += (size_t)gridDim.x * blockDim.x * 2) {
+        const float2 a = *reinterpret_cast<const float2*>(acc + i);
+        const uint32_t d = *reinterpret_cast<const uint32_t*>(dmul + i);
+        *reinterpret_cast<uint32_t*>(out + i) = pack_bf16x2(a.x * bf16_lo(d), a.y * bf16_hi(d));
+    }
+}
+
 }  // namespace onr
 
 // ------------------------------------------------------------------------------------------- host
@@ -632,8 +675,12 @@ struct onr_conv_plan {
     int grid;
     size_t smem;
     int* sched = nullptr;      // two device counters of the dynamic work-item feed (owned by the plan)
+    float* kacc = nullptr;     // split-K scratch (owned by the plan)
+    size_t kacc_elems = 0;
+    void* out = nullptr;       // split-K: final destination of the finishing kernel
     ~onr_conv_plan() {
         if (sched) cudaFree(sched);
+        if (kacc) cudaFree(kacc);
     }
 };
 
@@ -723,6 +770,23 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
         if (v == 1 || (v == 2 && block_n % 32 == 0)) p.cluster = v;
     }
     p.pair_tiles = ceil_div(p.px_tiles, p.cluster) * n_tiles;
+    // Split K for the data gradient of a SMALL layer: block 0's dgrad is two tiles with K = 9 x 800 channels — two
+    // CTAs issuing 540 N=32 MMAs each while 146 SMs idle (46 us, on the critical path).  Its (chunk, dw) K-groups are
+    // dealt out to ksplit work items per tile (>= 3 groups each) whose partial sums meet in an fp32 scratch
+    // (red.global.add); conv_split_finish_kernel applies the x SiLU' epilogue.  Measured on B200: the kernel itself goes
+    // from 43 to 20 us (block 0) and 23 to 20 us (block 1), but the training step does not move (1.2045 vs 1.1992 ms):
+    // by then the step waits for the side-stream chains (wgrad -> exchange -> fold backward of blocks 1 and 0), not for
+    // this kernel.  Hence opt-in: ONR_CONV_KSPLIT=1.
+    p.ksplit = 1;
+    p.kacc = nullptr;
+    if (d->kind == ONR_CONV_DGRAD && d->out_s == 1 && p.cluster == 1 && p.total_tiles * 2 <= num_sms() &&
+        getenv("ONR_CONV_KSPLIT") && atoi(getenv("ONR_CONV_KSPLIT")) == 1) {
+        const int groups = d->a_s * (d->a_s * d->a_cp / 64 + ((d->a_s * d->a_cp) % 64 ? 1 : 0)) * 3;
+        int ks = num_sms() / p.total_tiles;
+        if (ks > groups / 3) ks = groups / 3;
+        if (ks > 1) p.ksplit = ks;
+    }
+    p.pair_tiles *= p.ksplit;
     p.dynamic = 0;      // measured on B200: 1.193 (dynamic) vs 1.172 ms/step (static) - the static order keeps the L2 locality; knob only
     if (const char* e = getenv("ONR_CONV_DYNAMIC")) p.dynamic = (atoi(e) != 0 && p.cluster == 1) ? 1 : 0;
     p.sched = nullptr;
@@ -798,6 +862,18 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
         delete pl;
         return -1;
     }
+    if (p.ksplit > 1) {
+        pl->kacc_elems = (size_t)d->B * d->H * d->W * d->n_total;
+        cudaError_t e = cudaMalloc(&pl->kacc, pl->kacc_elems * sizeof(float));
+        if (e != cudaSuccess) {
+            set_error("conv plan: split-K scratch allocation failed: %s", cudaGetErrorString(e));
+            delete pl;
+            return (int)e;
+        }
+        p.kacc = pl->kacc;
+        pl->out = d->out;
+        pl->grid = p.pair_tiles < num_sms() ? p.pair_tiles : num_sms();
+    }
     if (p.dynamic) {
         cudaError_t e = cudaMalloc(&pl->sched, 2 * sizeof(int));
         if (e == cudaSuccess) e = cudaMemset(pl->sched, 0, 2 * sizeof(int));
@@ -815,6 +891,7 @@ int onr_conv_plan_create(onr_conv_plan** out, const onr_conv_desc* d) {
 int onr_conv_plan_run(const onr_conv_plan* pl, void* stream) {
     using namespace onr;
     ONR_REQUIRE(pl != nullptr, "null plan");
+    if (pl->p.ksplit > 1) ONR_CUDA(cudaMemsetAsync(pl->kacc, 0, pl->kacc_elems * sizeof(float), (cudaStream_t)stream));
     if (pl->p.cluster > 1) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(pl->grid);
@@ -835,6 +912,13 @@ int onr_conv_plan_run(const onr_conv_plan* pl, void* stream) {
             pl->tmA64, pl->tmA32, pl->tmB64, pl->tmB32, pl->tmY64, pl->tmY32, pl->tmD64, pl->tmD32, pl->p);
     }
     ONR_LAUNCH_CHECK();
+    if (pl->p.ksplit > 1) {
+        size_t blocks = (pl->kacc_elems / 2 + 255) / 256;
+        if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
+        conv_split_finish_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+            pl->kacc, pl->p.dmul, reinterpret_cast<__nv_bfloat16*>(pl->out), pl->kacc_elems);
+        ONR_LAUNCH_CHECK();
+    }
     return 0;
 }
 
