@@ -48,6 +48,13 @@ class WgradDesc(C.Structure):
     ]
 
 
+class BranchSet(C.Structure):
+    """onr_branch_set"""
+    _fields_ = [("cin", i32), ("cout", i32)] + \
+        [(n, vp) for n in ("w3x3", "b3x3", "w1x3", "b1x3", "w3x1", "b3x1", "w1x1", "b1x1", "seq_w1", "seq_w2", "avg_w")] + \
+        [(n, vp * 3) for n in ("edge_k0", "edge_b0", "edge_scale", "edge_bias", "edge_mask")]
+
+
 CONV_FPROP_TRAIN, CONV_FPROP_INFER, CONV_DGRAD, CONV_FPROP_Z, CONV_FPROP_HEAD = 0, 1, 2, 3, 4
 
 _SIGNATURES = {
@@ -56,6 +63,10 @@ _SIGNATURES = {
     "onr_check_device": (i32, []),
     "onr_launch_count": (C.c_ulonglong, []),
     "onr_pe_stem_fwd": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "onr_pe_stem_fwd_act": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
+    "onr_stem_bwd_act": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
+    "onr_stem_bwd_factors_act": (i32, [vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "onr_act_map": (i32, [vp, vp, sz, i32, i32, i32, vp]),
     "onr_pos_encoding": (i32, [vp, i32, vp, i32, vp, vp]),
     "onr_frame_u8_to_f32": (i32, [vp, sz, vp, vp]),
     "onr_stem_bwd": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
@@ -69,6 +80,8 @@ _SIGNATURES = {
     "onr_fold_plan_destroy": (None, [vp]),
     "onr_fold_plan_fwd": (i32, [vp] + [vp] * 9 + [vp, vp, vp]),
     "onr_fold_plan_bwd": (i32, [vp, vp, vp] + [vp] * 9 + [vp]),
+    "onr_branch_fold_fwd": (i32, [C.POINTER(BranchSet), vp, vp, vp]),
+    "onr_branch_fold_bwd": (i32, [C.POINTER(BranchSet), vp, vp, C.POINTER(BranchSet), vp]),
     "onr_tapmajor_permute": (i32, [vp, vp, i32, i32, i32, vp]),
     "onr_pack_weights_t": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
     "onr_unpack_wgrad_t": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
@@ -102,6 +115,8 @@ _SIGNATURES = {
     "onr_adam_max_tensors": (i32, []),
     "onr_adam_multi": (i32, [vp, i32, sz, vp, vp, vp, f32, f32, f32, f32, i32, vp]),
     "onr_sched_tick": (i32, [vp, vp, C.c_double, i32, i32, i32, i32, i32, vp]),
+    "onr_sched_tick_ex": (i32, [vp, vp, C.c_double, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "onr_mul_inplace_f32": (i32, [vp, vp, sz, vp]),
     "onr_abs_radix_hist": (i32, [vp, sz, u32, u32, i32, vp, vp]),
     "onr_apply_magnitude_mask": (i32, [vp, sz, f32, vp, vp, vp]),
     "onr_quant_rows": (i32, [vp, i32, sz, i32, vp, vp, vp, vp]),

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 # the fold / Adam kernels must track the fp32 reference; fast intrinsics are used explicitly where safe.
 
 LIB_SOURCES = [s for s in [
-    "onr_api.cu", "conv_igemm.cu", "wgrad_igemm.cu", "fold.cu", "fold_tc.cu", "stem.cu", "head.cu",
+    "onr_api.cu", "conv_igemm.cu", "wgrad_igemm.cu", "fold.cu", "fold_tc.cu", "fold_branches.cu", "stem.cu", "head.cu",
     "loss_ssim.cu", "adam.cu", "evalops.cu", "layout.cu",
 ] if os.path.exists(os.path.join(CSRC, s))]
 # test infrastructure (SIMT cross-check kernels, MMA issue microbenchmark): part of the self-test binary only

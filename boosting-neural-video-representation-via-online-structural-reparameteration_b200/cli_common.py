@@ -82,24 +82,28 @@ def build_parser(eval_mode=False):
     return p
 
 
-SUPPORTED = ("supported on the B200 hot path: --branch_type NeRV_vanilla|ERB, --act swish, --norm none, --single_res, "
+SUPPORTED = ("supported on the B200 hot path: --branch_type NeRV_vanilla|ERB (the north-star path) and ACB|RepVGG|DBB|ECB "
+             "(folded online into one convolution like ERB), every --act (swish is fused into the convolution, the "
+             "others take one extra elementwise pass), --norm none, --single_res, "
              "--num_blocks 1, --stem_dim_num <dim>_1, --conv_type conv, --loss_type L2|L1|SSIM|Fusion1..Fusion9, "
-             "--lr_type cosine|const|step, and block input widths (fc_hw_dim channels x expansion, then "
-             "max(width/reduction, lower_width)) of at most 128 channels; README recipe: --embed 1.25_40 "
+             "--lr_type cosine|const|step, --finetune with --prune_ratio < 1 (NeRV_vanilla|ERB); README recipe: --embed 1.25_40 "
              "--stem_dim_num 512_1 --fc_hw_dim 9_16_26 --expansion 1 --reduction 2 --lower_width 96 --strides 5 2 2 2 2 "
              "--single_res --act swish --loss Fusion6 --branch_type ERB")
 
 
 def validate_args(args):
-    """One clear error for every flag combination outside the hot path (the reference's own defaults — act gelu,
-    multi-resolution heads, fc dim 128 with expansion 8 — are among them), instead of a NotImplementedError or a plan
-    failure deep inside the first step."""
+    """One clear error for every flag combination outside the hot path (of the reference's own defaults the
+    multi-resolution heads are), instead of a NotImplementedError or a plan failure deep inside the first step."""
+    from .model import ACT_CODES, SUPPORTED_BRANCHES
     from .utils import LOSS_TERMS
     bad = []
-    if args.branch_type not in ('NeRV_vanilla', 'ERB'):
+    if args.branch_type not in SUPPORTED_BRANCHES:
         bad.append(f'--branch_type {args.branch_type}')
-    if args.act != 'swish':
+    if args.act not in ACT_CODES:
         bad.append(f'--act {args.act}')
+    if getattr(args, 'finetune', False) and args.prune_ratio < 1 and args.branch_type not in ('NeRV_vanilla', 'ERB'):
+        bad.append(f'--finetune with --branch_type {args.branch_type} (the reference handles NeRV_vanilla and ERB, '
+                   'main_eval.py:238, :297)')
     if args.norm != 'none':
         bad.append(f'--norm {args.norm}')
     if not args.single_res:
@@ -113,15 +117,7 @@ def validate_args(args):
     try:
         if int(str(args.stem_dim_num).split('_')[1]) != 1:
             bad.append(f'--stem_dim_num {args.stem_dim_num}')
-        width = int(str(args.fc_hw_dim).split('_')[2])
-        widths = []
-        for i, s in enumerate(args.strides):
-            widths.append(width)
-            width = int(width * args.expansion) if i == 0 else max(width // (1 if s == 1 else args.reduction),
-                                                                     args.lower_width)
-        if max(widths) > 128:
-            bad.append(f'block input width {max(widths)} > 128 channels (fc_hw_dim {args.fc_hw_dim}, expansion '
-                       f'{args.expansion})')
+        int(str(args.fc_hw_dim).split('_')[2])
     except (IndexError, ValueError):
         bad.append(f'--stem_dim_num {args.stem_dim_num} / --fc_hw_dim {args.fc_hw_dim}')
     if bad:

@@ -114,12 +114,16 @@ adam_multi_kernel(const AdamEntry* __restrict__ table, int n_tensors, const floa
 // One thread: t = ++step; lr(t) per adjust_lr (reference utils.py:240-259) evaluated in double like Python.
 // The t-th optimizer step is iteration i = (t-1) % steps_per_epoch of epoch (t-1) / steps_per_epoch and uses
 // cur_epoch = epoch + i / data_size (data_size = len(dataset), main_train.py:216, :247).
+// epoch_offset / epoch_mod: the prune-then-finetune loop (reference main_eval.py:446-466) restarts the optimizer (Adam
+// step count from 1) but continues the epoch numbering at the checkpoint's epoch and evaluates
+// adjust_lr(epoch % (start_epoch + finetune_epochs)) against the ORIGINAL --epochs / warm-up.
 __global__ void sched_tick_kernel(int* __restrict__ step_dev, float* __restrict__ lr_dev, double lr0,
-                                  int steps_per_epoch, int data_size, int warmup, int epochs, int lr_type) {
+                                  int steps_per_epoch, int data_size, int warmup, int epochs, int lr_type,
+                                  int epoch_offset, int epoch_mod) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int t = *step_dev + 1;
     *step_dev = t;
-    const int epoch = ((t - 1) / steps_per_epoch) % epochs;
+    const int epoch = (epoch_offset + (t - 1) / steps_per_epoch) % epoch_mod;
     const int it = (t - 1) % steps_per_epoch;
     const double e = (double)epoch + (double)it / (double)data_size;
     double mult = 1.0;
@@ -136,7 +140,19 @@ extern "C" int onr_sched_tick(int* step_dev, float* lr_dev, double lr0, int step
     ONR_REQUIRE(steps_per_epoch >= 1 && data_size >= 1 && epochs >= 1 && (lr_type == 0 || lr_type == 1),
                 "sched_tick: bad schedule (lr_type 0 = cosine, 1 = const)");
     sched_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_dev, lr_dev, lr0, steps_per_epoch, data_size, warmup,
-                                                         epochs, lr_type);
+                                                         epochs, lr_type, 0, epochs);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int onr_sched_tick_ex(int* step_dev, float* lr_dev, double lr0, int steps_per_epoch, int data_size,
+                                 int warmup, int epochs, int lr_type, int epoch_offset, int epoch_mod, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(steps_per_epoch >= 1 && data_size >= 1 && epochs >= 1 && (lr_type == 0 || lr_type == 1),
+                "sched_tick: bad schedule (lr_type 0 = cosine, 1 = const)");
+    ONR_REQUIRE(epoch_offset >= 0 && epoch_mod >= 1, "sched_tick: bad epoch offset / modulus");
+    sched_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_dev, lr_dev, lr0, steps_per_epoch, data_size, warmup,
+                                                         epochs, lr_type, epoch_offset, epoch_mod);
     ONR_LAUNCH_CHECK();
     return 0;
 }

@@ -99,6 +99,22 @@ __global__ void frame_u8_to_f32_kernel(const uint8_t* __restrict__ src, size_t n
         dst[i] = __fdiv_rn((float)src[i], 255.0f);
 }
 
+// g[i] *= m[i]: the gradient side of torch.nn.utils.prune's `weight = weight_orig * weight_mask` re-parameterisation
+// (reference main_eval.py:213-545, prune-then-finetune), applied to the whole flat gradient buffer in one pass.
+__global__ void mul_inplace_kernel(float* __restrict__ g, const float* __restrict__ m, size_t n) {
+    const size_t n4 = n / 4;
+    float4* g4 = reinterpret_cast<float4*>(g);
+    const float4* m4 = reinterpret_cast<const float4*>(m);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = g4[i];
+        const float4 b = __ldg(m4 + i);
+        a.x *= b.x; a.y *= b.y; a.z *= b.z; a.w *= b.w;
+        g4[i] = a;
+    }
+    for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        g[i] *= m[i];
+}
+
 static inline int grid1d(size_t n) {
     size_t g = (n + 255) / 256;
     const size_t cap = (size_t)num_sms() * 8;
@@ -121,6 +137,16 @@ int onr_abs_radix_hist(const float* w, size_t n, uint32_t prefix, uint32_t prefi
 int onr_apply_magnitude_mask(const float* w, size_t n, float thr, float* mask, float* w_out, void* stream) {
     using namespace onr;
     magnitude_mask_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(w, n, thr, mask, w_out);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
+
+int onr_mul_inplace_f32(float* g, const float* m, size_t n, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(g != nullptr && m != nullptr, "mul_inplace: null argument");
+    ONR_REQUIRE(((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0, "mul_inplace: buffers must be 16-byte aligned");
+    if (n == 0) return 0;
+    mul_inplace_kernel<<<grid1d((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(g, m, n);
     ONR_LAUNCH_CHECK();
     return 0;
 }

@@ -111,6 +111,7 @@ static const Shape kShapes[] = {
     {"b2", 2, 19, 35, 96, 96, 2},         // batch 2, odd sizes
     {"u3", 1, 16, 32, 96, 96, 3},         // stride 3 (UVG 1080p block 1): N = 864
     {"wide", 1, 9, 16, 128, 128, 5},      // NeRV-L width block 0: N = 3200
+    {"xl", 1, 12, 20, 160, 96, 2},        // more than 128 input channels: wgrad channel chunks (128 + 32)
     {"l3", 1, 180, 320, 96, 96, 2},
     {"l4", 1, 360, 640, 96, 96, 2},       // Bunny 720p last block (timing)
 };

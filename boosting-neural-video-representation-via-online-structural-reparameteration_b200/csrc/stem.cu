@@ -7,12 +7,17 @@
 // Backward: rank-1 gW2, W2^T g for dh1, then the 80x512 layer.
 // W2 (7.7 MB at fc 9_16_26, 33 MB at 9_16_112) is read exactly once per pass with 128-bit loads.
 #include "onr_common.cuh"
+#include "act.cuh"
 
 namespace onr {
 
+// `act`: activation code of act.cuh (reference MLP(act=...), model.py:174-188).  Code 0 (swish, the north-star
+// configuration) keeps its original expressions bit for bit; the other codes go through act_value_grad.
+
 __global__ void pe_layer1_kernel(const float* __restrict__ t_norm, const float* __restrict__ freqs, int levels,
                                  const float* __restrict__ W1, const float* __restrict__ b1, int hid,
-                                 float* __restrict__ embed, float* __restrict__ pre1, float* __restrict__ h1) {
+                                 float* __restrict__ embed, float* __restrict__ pre1, float* __restrict__ h1,
+                                 int act) {
     extern __shared__ float se[];  // [2*levels]
     const int b = blockIdx.x;
     const int E = 2 * levels;
@@ -38,7 +43,12 @@ __global__ void pe_layer1_kernel(const float* __restrict__ t_norm, const float* 
         for (int e = 0; e < E; ++e) acc = fmaf(w[e], se[e], acc);
         acc += b1[j];
         pre1[(size_t)b * hid + j] = acc;
-        h1[(size_t)b * hid + j] = acc / (1.0f + expf(-acc));
+        float hv = acc / (1.0f + expf(-acc));
+        if (act != 0) {
+            float dd;
+            act_value_grad(acc, act, &hv, &dd);
+        }
+        h1[(size_t)b * hid + j] = hv;
     }
 }
 
@@ -55,7 +65,7 @@ __global__ void pos_encoding_kernel(const float* __restrict__ t_norm, int B, con
 // one warp per output position p = (h*fw + w)*Cp + c of the NHWC stem output
 __global__ void stem_layer2_kernel(const float* __restrict__ h1, int B, int hid, const float* __restrict__ W2,
                                    const float* __restrict__ b2, int fc_dim, int fh, int fw, int Cp,
-                                   __nv_bfloat16* __restrict__ x0, __nv_bfloat16* __restrict__ dstem) {
+                                   __nv_bfloat16* __restrict__ x0, __nv_bfloat16* __restrict__ dstem, int act) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int total = fh * fw * Cp;
@@ -86,9 +96,11 @@ __global__ void stem_layer2_kernel(const float* __restrict__ h1, int B, int hid,
             if (lane == 0) {
                 const float z = acc + b2[o];
                 const float sg = 1.0f / (1.0f + expf(-z));
-                const float y = z * sg;
+                float y = z * sg;
+                float dy = sg + y * (1.0f - sg);
+                if (act != 0) act_value_grad(z, act, &y, &dy);
                 x0[(size_t)b * total + p] = __float2bfloat16(y);
-                dstem[(size_t)b * total + p] = __float2bfloat16(sg + y * (1.0f - sg));
+                dstem[(size_t)b * total + p] = __float2bfloat16(dy);
             }
         }
     }
@@ -186,7 +198,7 @@ stem_bwd_layer2_b1_kernel(const __nv_bfloat16* __restrict__ g0, const float* __r
 
 __global__ void stem_bwd_layer1_kernel(const float* __restrict__ dh1, const float* __restrict__ pre1,
                                        const float* __restrict__ embed, int B, int hid, int E,
-                                       float* __restrict__ gW1, float* __restrict__ gb1) {
+                                       float* __restrict__ gW1, float* __restrict__ gb1, int act) {
     // one thread per (j, e) pair plus bias; sums over the batch
     const int total = hid * E;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -195,7 +207,12 @@ __global__ void stem_bwd_layer1_kernel(const float* __restrict__ dh1, const floa
         for (int b = 0; b < B; ++b) {
             const float z = pre1[(size_t)b * hid + j];
             const float sg = 1.0f / (1.0f + expf(-z));
-            const float dpre = dh1[(size_t)b * hid + j] * (sg + z * sg * (1.0f - sg));
+            float da = sg + z * sg * (1.0f - sg);
+            if (act != 0) {
+                float yy;
+                act_value_grad(z, act, &yy, &da);
+            }
+            const float dpre = dh1[(size_t)b * hid + j] * da;
             gw = fmaf(dpre, embed[(size_t)b * E + e], gw);
             gb += dpre;
         }
@@ -250,14 +267,19 @@ stem_factors_local_kernel(const __nv_bfloat16* __restrict__ g0, const float* __r
 __global__ void stem_factors_tail_kernel(const float* __restrict__ h1, const float* __restrict__ dh1,
                                          const float* __restrict__ pre1, const float* __restrict__ embed, int hid, int E,
                                          float* __restrict__ slot_h1, float* __restrict__ slot_dpre1,
-                                         float* __restrict__ slot_embed) {
+                                         float* __restrict__ slot_embed, int act) {
     const int n = hid > E ? hid : E;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         if (j < hid) {
             const float z = pre1[j];
             const float sg = 1.0f / (1.0f + expf(-z));
+            float da = sg + z * sg * (1.0f - sg);
+            if (act != 0) {
+                float yy;
+                act_value_grad(z, act, &yy, &da);
+            }
             slot_h1[j] = h1[j];
-            slot_dpre1[j] = dh1[j] * (sg + z * sg * (1.0f - sg));
+            slot_dpre1[j] = dh1[j] * da;
         }
         if (j < E) slot_embed[j] = embed[j];
     }
@@ -317,7 +339,15 @@ size_t onr_stem_factor_floats(int fc_dim, int fh, int fw, int hid, int emb_len) 
 int onr_stem_bwd_factors(const void* g0, const float* embed, int emb_len, const float* pre1, const float* h1, int hid,
                          const float* W2, int fc_dim, int fh, int fw, int Cp, float* slot, float* scratch_dh1,
                          void* stream) {
+    return onr_stem_bwd_factors_act(g0, embed, emb_len, pre1, h1, hid, W2, fc_dim, fh, fw, Cp, slot, scratch_dh1, 0,
+                                    stream);
+}
+
+int onr_stem_bwd_factors_act(const void* g0, const float* embed, int emb_len, const float* pre1, const float* h1,
+                             int hid, const float* W2, int fc_dim, int fh, int fw, int Cp, float* slot,
+                             float* scratch_dh1, int act, void* stream) {
     using namespace onr;
+    ONR_REQUIRE(act >= 0 && act < kActCount, "stem: unknown activation code %d", act);
     ONR_REQUIRE(hid % 4 == 0 && hid <= 128 * 4 * kStemFastU, "stem factors: unsupported widths");
     cudaStream_t st = (cudaStream_t)stream;
     const int n_out = fc_dim * fh * fw;
@@ -326,7 +356,7 @@ int onr_stem_bwd_factors(const void* g0, const float* embed, int emb_len, const 
         reinterpret_cast<const __nv_bfloat16*>(g0), W2, hid, fc_dim, fh, fw, Cp, slot, scratch_dh1);
     ONR_LAUNCH_CHECK();
     stem_factors_tail_kernel<<<ceil_div(hid > emb_len ? hid : emb_len, 256), 256, 0, st>>>(h1, scratch_dh1, pre1, embed, hid, emb_len,
-                                                                 slot + n_out, slot + n_out + hid, slot + n_out + 2 * hid);
+                                                                 slot + n_out, slot + n_out + hid, slot + n_out + 2 * hid, act);
     ONR_LAUNCH_CHECK();
     return 0;
 }
@@ -351,11 +381,19 @@ int onr_stem_grads_from_factors(const float* slots, int K, int emb_len, int hid,
 int onr_pe_stem_fwd(const float* t_norm, int B, const float* freqs, int levels, const float* W1,
                     const float* b1, int hid, const float* W2, const float* b2, int fc_dim, int fh, int fw,
                     int Cp, float* embed, float* pre1, float* h1, void* x0, void* dstem, void* stream) {
+    return onr_pe_stem_fwd_act(t_norm, B, freqs, levels, W1, b1, hid, W2, b2, fc_dim, fh, fw, Cp, embed, pre1, h1, x0,
+                               dstem, 0, stream);
+}
+
+int onr_pe_stem_fwd_act(const float* t_norm, int B, const float* freqs, int levels, const float* W1,
+                        const float* b1, int hid, const float* W2, const float* b2, int fc_dim, int fh, int fw,
+                        int Cp, float* embed, float* pre1, float* h1, void* x0, void* dstem, int act, void* stream) {
     using namespace onr;
+    ONR_REQUIRE(act >= 0 && act < kActCount, "stem: unknown activation code %d", act);
     ONR_REQUIRE(B >= 1 && levels >= 1 && hid % 4 == 0 && Cp % 32 == 0 && Cp >= fc_dim, "stem: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     pe_layer1_kernel<<<B, 256, 2 * levels * sizeof(float), st>>>(t_norm, freqs, levels, W1, b1, hid, embed,
-                                                                 pre1, h1);
+                                                                 pre1, h1, act);
     ONR_LAUNCH_CHECK();
     const int total = fh * fw * Cp;
     const int wpb = 8;
@@ -363,7 +401,7 @@ int onr_pe_stem_fwd(const float* t_norm, int B, const float* freqs, int levels, 
     if (grid > num_sms() * 8) grid = num_sms() * 8;
     stem_layer2_kernel<<<grid, wpb * 32, 0, st>>>(h1, B, hid, W2, b2, fc_dim, fh, fw, Cp,
                                                   reinterpret_cast<__nv_bfloat16*>(x0),
-                                                  reinterpret_cast<__nv_bfloat16*>(dstem));
+                                                  reinterpret_cast<__nv_bfloat16*>(dstem), act);
     ONR_LAUNCH_CHECK();
     return 0;
 }
@@ -380,7 +418,15 @@ int onr_pos_encoding(const float* t_norm, int B, const float* freqs, int levels,
 int onr_stem_bwd(const void* g0, int B, const float* embed, int emb_len, const float* pre1, const float* h1,
                  int hid, const float* W2, int fc_dim, int fh, int fw, int Cp, float* gW1, float* gb1,
                  float* gW2, float* gb2, float* scratch_dh1, void* stream) {
+    return onr_stem_bwd_act(g0, B, embed, emb_len, pre1, h1, hid, W2, fc_dim, fh, fw, Cp, gW1, gb1, gW2, gb2,
+                            scratch_dh1, 0, stream);
+}
+
+int onr_stem_bwd_act(const void* g0, int B, const float* embed, int emb_len, const float* pre1, const float* h1,
+                     int hid, const float* W2, int fc_dim, int fh, int fw, int Cp, float* gW1, float* gb1,
+                     float* gW2, float* gb2, float* scratch_dh1, int act, void* stream) {
     using namespace onr;
+    ONR_REQUIRE(act >= 0 && act < kActCount, "stem: unknown activation code %d", act);
     ONR_REQUIRE(hid <= 128 * kStemMaxJ, "stem: hidden width %d too large", hid);
     cudaStream_t st = (cudaStream_t)stream;
     ONR_CUDA(cudaMemsetAsync(scratch_dh1, 0, (size_t)B * hid * sizeof(float), st));
@@ -395,7 +441,7 @@ int onr_stem_bwd(const void* g0, int B, const float* embed, int emb_len, const f
     }
     ONR_LAUNCH_CHECK();
     stem_bwd_layer1_kernel<<<ceil_div(hid * emb_len, 256), 256, 0, st>>>(scratch_dh1, pre1, embed, B, hid,
-                                                                        emb_len, gW1, gb1);
+                                                                        emb_len, gW1, gb1, act);
     ONR_LAUNCH_CHECK();
     return 0;
 }

@@ -14,6 +14,10 @@
 // Accumulators: 3 x Cin_p fp32 columns of TMEM.  Partial sums of the image slices are combined with
 // red.global.add.v4.f32 into dKp (zeroed by the caller).
 //
+// Input channels beyond 128 (fc dim 128 with expansion 8, fc_hw_dim 9_16_156, ...): the X channels are cut into
+// chunks of <= 128 and the chunk index becomes one more job coordinate — every chunk is an independent GEMM over the
+// same dZ rows that owns the columns [c0, c0 + cc) of dKp; chunk 0 also carries the bias column.
+//
 // Bias gradient for free: in the kw = 1 jobs the centre-tap (kh = 1) MMAs see a B operand that is 32 channels
 // wider — a constant tile whose channel 0 is 1.0 — so one extra accumulator column collects
 // dbias_p[n] = sum_pixels dZ[pixel, n] on the tensor pipe (+11 % MMA work in one of three jobs) instead of a
@@ -34,7 +38,8 @@ constexpr int kWgRowsPerUnit = 24;
 struct WgradParams {
     int B, H, W;
     int s, jc_chunks, n_pre, n_tiles;
-    int xb, x_cp;
+    int xb, x_cp;          // xb: X boxes per stage of a full chunk; x_cp: ALL padded input channels (pitch of dKp)
+    int nchunks;           // ceil(x_cp / 128)
     int wchunks, hunits, units_total, splits, rows_per_unit;
     float* dKp;
     float* dbias_p;
@@ -58,7 +63,11 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int job = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
-    const int n_tile = job / 3, kw = job % 3;
+    const int chunk = job / (p.n_tiles * 3), jj = job % (p.n_tiles * 3);
+    const int n_tile = jj / 3, kw = jj % 3;
+    const int c0 = chunk * 128;                              // first X channel of this CTA's chunk
+    const int cc = min(128, p.x_cp - c0);                    // its width (multiple of 32)
+    const int xbc = cc / 32;
     const int u0 = (int)((long long)split * p.units_total / p.splits);
     const int u1 = (int)((long long)(split + 1) * p.units_total / p.splits);
 
@@ -112,7 +121,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
                         const uint32_t dz_s = smem_base + stage * stage_bytes;
                         const uint32_t x_s = dz_s + 4 * kWgBox;
                         const bool with_x = r >= r0;
-                        mbar_expect_tx(full, (with_x ? (4 + p.xb) : 4) * kWgBox);
+                        mbar_expect_tx(full, (with_x ? (4 + xbc) : 4) * kWgBox);
                         // dZ row r+1, four 32-channel boxes of this CTA's 128-channel n tile
                         for (int qb = 0; qb < 4; ++qb) {
                             const int qn = n_tile * 4 + qb;  // 32-channel chunk of n'
@@ -121,8 +130,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
                             tma_load_5d(dz_s + qb * kWgBox, &tmDz, full, jc0, wbase, ii, r + 1, b);
                         }
                         if (with_x)
-                            for (int xb = 0; xb < p.xb; ++xb)
-                                tma_load_5d(x_s + xb * kWgBox, &tmX, full, xb * 32, wbase + kw - 1, 0, r, b);
+                            for (int xb = 0; xb < xbc; ++xb)
+                                tma_load_5d(x_s + xb * kWgBox, &tmX, full, c0 + xb * 32, wbase + kw - 1, 0, r, b);
                     }
                     __syncwarp();
                 }
@@ -130,8 +139,10 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
         }
     } else if (warp == kWgWarpMma) {
         {
-            const uint32_t idesc = make_idesc_bf16(128, p.x_cp, 1, 1);
-            const uint32_t idesc_b = make_idesc_bf16(128, p.x_cp + 32, 1, 1);   // centre tap + ones column
+            const uint32_t idesc = make_idesc_bf16(128, cc, 1, 1);
+            // centre tap + ones column: chunk 0 only (a full chunk whenever there are several, so the constant box
+            // at (4 + p.xb) * kWgBox directly follows its X boxes)
+            const uint32_t idesc_b = chunk == 0 ? make_idesc_bf16(128, cc + 32, 1, 1) : idesc;
             uint32_t g = 0;
             uint32_t started = 0;  // bit kh set once acc[kh] holds data
             for (int u = u0; u < u1; ++u) {
@@ -155,7 +166,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
                                 const uint64_t adesc = make_smem_desc(dz_s + kk * 1024, kWgBox, 512, SWZ_64B);
                                 const uint64_t bdesc = make_smem_desc(x_s + kk * 1024, kWgBox, 512, SWZ_64B);
                                 // accumulator columns: kh=0 -> [0,Cp), kh=2 -> [Cp,2Cp), kh=1 -> [2Cp, 3Cp(+32))
-                                const uint32_t col = kh == 0 ? 0u : (kh == 2 ? (uint32_t)p.x_cp : 2u * p.x_cp);
+                                const uint32_t col = kh == 0 ? 0u : (kh == 2 ? (uint32_t)cc : 2u * cc);
                                 umma_bf16(tmem_base + col, adesc, bdesc, (kh == 1 && kw == 1) ? idesc_b : idesc,
                                           ((started >> kh) & 1u) | (kk != 0));
                             }
@@ -176,15 +187,15 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
         const int n = n_tile * 128 + row;
         mbar_wait(smem_u32(&bars->acc_full), 0);
         tc_fence_after();
-        const int cchunks = p.x_cp / 32;
+        const int cchunks = cc / 32;
         for (int kh = 0; kh < 3; ++kh) {
-            const uint32_t colb = kh == 0 ? 0u : (kh == 2 ? (uint32_t)p.x_cp : 2u * p.x_cp);
+            const uint32_t colb = kh == 0 ? 0u : (kh == 2 ? (uint32_t)cc : 2u * cc);
             for (int c = 0; c < cchunks; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + colb + c * 32, r);
                 tmem_ld_wait();
                 if (n < p.n_pre) {
-                    float* dst = p.dKp + ((size_t)n * 9 + kh * 3 + kw) * p.x_cp + c * 32;
+                    float* dst = p.dKp + ((size_t)n * 9 + kh * 3 + kw) * p.x_cp + c0 + c * 32;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst + j * 4),
@@ -194,9 +205,9 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_consta
                 }
             }
         }
-        if (kw == 1 && p.dbias_p != nullptr) {
+        if (kw == 1 && chunk == 0 && p.dbias_p != nullptr) {
             uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + 3u * p.x_cp, r);
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + 3u * cc, r);
             tmem_ld_wait();
             if (n < p.n_pre) atomicAdd(p.dbias_p + n, __uint_as_float(r[0]));
         }
@@ -227,7 +238,8 @@ extern "C" {
 int onr_wgrad_plan_create(onr_wgrad_plan** out, const onr_wgrad_desc* d) {
     using namespace onr;
     ONR_REQUIRE(out && d, "null argument");
-    ONR_REQUIRE(d->x_cp % 32 == 0 && d->dz_cp % 32 == 0 && d->x_cp <= 128, "wgrad: unsupported channels");
+    ONR_REQUIRE(d->x_cp % 32 == 0 && d->dz_cp % 32 == 0 && d->x_cp >= 32 && d->dz_cp >= 32,
+                "wgrad: channel counts must be positive multiples of 32 (x_cp %d dz_cp %d)", d->x_cp, d->dz_cp);
     ONR_REQUIRE(d->s >= 1 && d->B >= 1 && d->H >= 1 && d->W >= 1, "wgrad: bad grid");
     onr_wgrad_plan* pl = new onr_wgrad_plan();
     WgradParams& p = pl->p;
@@ -236,13 +248,14 @@ int onr_wgrad_plan_create(onr_wgrad_plan** out, const onr_wgrad_desc* d) {
     p.jc_chunks = d->s * d->dz_cp / 32;
     p.n_pre = d->s * d->s * d->dz_cp;
     p.n_tiles = ceil_div(p.n_pre, 128);
-    p.xb = d->x_cp / 32;
     p.x_cp = d->x_cp;
+    p.nchunks = ceil_div(d->x_cp, 128);
+    p.xb = (d->x_cp < 128 ? d->x_cp : 128) / 32;
     p.wchunks = ceil_div(d->W, kWgPx);
     p.rows_per_unit = kWgRowsPerUnit;
     p.hunits = ceil_div(d->H, p.rows_per_unit);
     p.units_total = d->B * p.wchunks * p.hunits;
-    const int jobs = p.n_tiles * 3;
+    const int jobs = p.nchunks * p.n_tiles * 3;
     int splits = num_sms() / jobs;
     if (splits < 1) splits = 1;
     if (splits > p.units_total) splits = p.units_total;

@@ -18,7 +18,7 @@ import os
 
 import torch
 
-from . import _lib
+from . import _lib, branches
 from ._lib import ConvDesc, WgradDesc, check, ptr
 
 
@@ -152,14 +152,19 @@ class NetExecutor:
         # kernels evaluate SiLU(z) / SiLU'(z) themselves — its output feeds nothing else, so the SiLU' map (177 MB at
         # 720p) is never written and the block's epilogue, which set the pace of that kernel, shrinks to bias + convert.
         self._head_fused = os.environ.get("ONR_HEAD_FUSED", "1") != "0"
-        self._last_z = (train and B == 1 and (self.H * self.W) % 4 == 0 and self._head_fused
+        # activation code of the run (csrc/act.cuh).  swish (0) is fused into the convolution epilogue; any other
+        # activation runs the blocks in pre-activation mode (ONR_CONV_FPROP_Z) followed by onr_act_map, and the
+        # swish-only shortcuts (z-only last block, fused decode head) are off
+        self.act = int(getattr(gen, "act_code", 0))
+        swish = self.act == 0
+        self._last_z = (swish and train and B == 1 and (self.H * self.W) % 4 == 0 and self._head_fused
                         and os.environ.get("ONR_LAST_Z", "1") != "0" and os.environ.get("ONR_HEAD_STREAM", "1") != "0")
         # Decode with the RGB head fused into the last block's epilogue (ONR_CONV_FPROP_HEAD; ONR_DECODE_FUSED=1): the last
         # activation (177 MB at 720p) is never written, only the image is.  Measured on B200 it is NOT faster — the fused
         # kernel needs one 96-wide N tile per sub-pixel and takes 0.221 ms against 0.177 + 0.044 ms for the 128-wide
         # convolution plus the streaming head kernel (2853 vs 2890 frames/s) — so it is an option that saves memory,
         # not the default.
-        self._decode_fused = ((not train) and pad32(self.C_last) <= 256
+        self._decode_fused = (swish and (not train) and pad32(self.C_last) <= 256
                               and os.environ.get("ONR_DECODE_FUSED", "0") == "1")
         # ---- activations: x[l] is the input of block l (x[L] = last block output, or its pre-activation) ----
         self.x, self.d, self.dz = [], [], []
@@ -194,10 +199,12 @@ class NetExecutor:
             pool_off.append((a, b))
         self._wgrad_pool = zeros(total) if train else None
         for (g, blk), (off_k, off_b) in zip(zip(self.geoms, gen.layers), pool_off):
-            erb = blk.is_erb_train()
+            kind = blk.fold_kind()
+            erb = kind == "erb"
             # folded kernel: tap-major [Cout][9][Cin] on the tensor-core path, OIHW on the SIMT path (ONR_FOLD_SIMT=1)
-            self.K.append(zeros(g.cout, g.cin, 3, 3) if erb else None)
-            self.bias.append(zeros(g.cout) if erb else None)
+            # and for the ACB / RepVGG / DBB / ECB branch sets (fold_branches.cu)
+            self.K.append(zeros(g.cout, g.cin, 3, 3) if kind else None)
+            self.bias.append(zeros(g.cout) if kind else None)
             self.T.append(zeros(g.cout, g.cin, 3, 3) if (erb and not self._fold_tc) else None)
             self.fold.append(FoldPlan(self.lib, g.cin, g.cout, train, dev) if (erb and self._fold_tc) else None)
             self.wf.append(zeros(9, g.npad, g.cpi, dtype=bf16))
@@ -223,7 +230,8 @@ class NetExecutor:
         self.fprop, self.dgrad, self.wgrad = [], [], []
         for l, g in enumerate(self.geoms):
             last_z = self._last_z and l == L - 1
-            kind = _lib.CONV_FPROP_Z if last_z else (_lib.CONV_FPROP_TRAIN if train else _lib.CONV_FPROP_INFER)
+            kind = _lib.CONV_FPROP_Z if (last_z or not swish) else (_lib.CONV_FPROP_TRAIN if train
+                                                                     else _lib.CONV_FPROP_INFER)
             extra = {}
             if self._decode_fused and l == L - 1:
                 head = gen.head_conv()
@@ -234,7 +242,8 @@ class NetExecutor:
                 lib, kind=kind, B=B, H=g.h, W=g.w, a=ptr(self.x[l]), a_cp=g.cpi, a_s=1,
                 w=ptr(self.wf[l]), n_rows=g.npad, n_total=g.nk,
                 out=ptr(self.x[l + 1]), out_cp=g.cpo, out_s=g.s,
-                out_d=ptr(self.d[l + 1]) if (train and not last_z) else None, bias_p=ptr(self.bias_p[l]), dmul=None,
+                out_d=ptr(self.d[l + 1]) if (train and swish and not last_z) else None, bias_p=ptr(self.bias_p[l]),
+                dmul=None,
                 **extra))
             if train:
                 self.dgrad.append(_conv_plan(
@@ -256,6 +265,9 @@ class NetExecutor:
         blk = self.gen.layers[l]
         g = self.geoms[l]
         st = _lib.stream()
+        if blk.fold_kind() == "set":
+            branches.fold_fwd(self.lib, blk, self.K[l], self.bias[l], st)
+            return self.K[l], self.bias[l], False
         if blk.is_erb_train():
             if self._fold_tc:
                 self.fold[l].fwd(blk, self.K[l], self.bias[l], st)
@@ -281,7 +293,9 @@ class NetExecutor:
         """Identity + version of every tensor the packed operands depend on (decode-time cache key)."""
         key = []
         for blk in self.gen.layers:
-            if blk.is_erb_train():
+            if blk.fold_kind() == "set":
+                ts = [t for _, _, t in branches.branch_slots(blk)]
+            elif blk.is_erb_train():
                 ts = [getattr(blk, n).weight for n in ("rbr_3x3_branch", "rbr_1x3_branch", "rbr_3x1_branch",
                       "rbr_1x1_3x3_1x1_branch_1x1_1", "rbr_1x1_3x3_1x1_branch_3x3", "rbr_1x1_3x3_1x1_branch_1x1_2")]
                 ts += [blk.rbr_3x3_branch.bias, blk.rbr_1x3_branch.bias, blk.rbr_3x1_branch.bias]
@@ -361,11 +375,11 @@ class NetExecutor:
             self.embed.copy_(embed.reshape(self.B, self.E))
         elif freqs is None:
             raise ValueError("t_norm needs the frequency table of the PositionalEncoding")
-        check(self.lib.onr_pe_stem_fwd(
+        check(self.lib.onr_pe_stem_fwd_act(
             ptr(t_norm), self.B, ptr(freqs), self.E // 2,
             ptr(lin1.weight), ptr(lin1.bias), self.hid, ptr(lin2.weight), ptr(lin2.bias),
             gen.fc_dim, gen.fc_h, gen.fc_w, g0.cpi,
-            ptr(self.embed), ptr(self.pre1), ptr(self.h1), ptr(self.x[0]), ptr(self.d[0]), st),
+            ptr(self.embed), ptr(self.pre1), ptr(self.h1), ptr(self.x[0]), ptr(self.d[0]), self.act, st),
             "onr_pe_stem_fwd")
         main = torch.cuda.current_stream()
         head = gen.head_conv()
@@ -376,6 +390,10 @@ class NetExecutor:
             if events is not None:
                 main.wait_event(events[l])
             check(self.lib.onr_conv_plan_run(self.fprop[l].handle, st), "onr_conv_plan_run(fprop)")
+            if self.act != 0:
+                g = self.geoms[l]
+                check(self.lib.onr_act_map(ptr(self.x[l + 1]), ptr(self.d[l + 1]) if self.train else None,
+                                           self.B * g.ho * g.wo, g.cnew, g.cpo, self.act, st), "onr_act_map")
         if self._decode_fused:
             return self.img
         head_fwd = self.lib.onr_head_fwd_z if self._last_z else self.lib.onr_head_fwd
@@ -476,7 +494,8 @@ class NetExecutor:
                 if self._wgrad_on_side:
                     side.wait_event(pool_clear)
                     check(lib.onr_wgrad_plan_run(self.wgrad[l].handle, sst), "onr_wgrad_plan_run")
-                if blk.is_erb_train():
+                folded = blk.fold_kind() is not None
+                if folded:
                     dK, db = self.dK[l], self.dbias[l]
                 else:   # single-branch block: dK is the parameter gradient itself (grads are zero on entry)
                     name = f"layers.{l}." + blk.single_conv_name()
@@ -485,9 +504,9 @@ class NetExecutor:
                 check(unpack(ptr(self.dKp[l]), ptr(self.dbias_p[l]), g.cin, g.cnew, g.s, ptr(dK), ptr(db), sst),
                       "onr_unpack_wgrad")
                 if reduce is not None:
-                    reduce(self.dKb[l] if blk.is_erb_train() else
+                    reduce(self.dKb[l] if folded else
                            self._flat_span(grads, [name + ".weight", name + ".bias"]))
-                if blk.is_erb_train():
+                if folded:
                     self.scatter_block_grads(l, grads)
                 ev = torch.cuda.Event()
                 ev.record(side)
@@ -510,20 +529,21 @@ class NetExecutor:
             # data-parallel, one frame per rank: exchange the rank-1 FACTORS of the stem gradients (an all-gather of
             # ~21 KB per rank) instead of all-reducing the 7.7 .. 33 MB matrices at the very end of the backward
             slots, rank, world = reduce.stem_slots(self)
-            check(lib.onr_stem_bwd_factors(
+            check(lib.onr_stem_bwd_factors_act(
                 ptr(self.dz[0]), ptr(self.embed), self.E, ptr(self.pre1), ptr(self.h1), self.hid, ptr(lin2.weight),
-                gen.fc_dim, gen.fc_h, gen.fc_w, g0.cpi, ptr(slots[rank]), ptr(self.dh1), st), "onr_stem_bwd_factors")
+                gen.fc_dim, gen.fc_h, gen.fc_w, g0.cpi, ptr(slots[rank]), ptr(self.dh1), self.act, st),
+                "onr_stem_bwd_factors")
             gather(slots, rank)
             check(lib.onr_stem_grads_from_factors(
                 ptr(slots), world, self.E, self.hid, gen.fc_dim, gen.fc_h, gen.fc_w,
                 ptr(grads["stem.0.weight"]), ptr(grads["stem.0.bias"]), ptr(grads["stem.2.weight"]),
                 ptr(grads["stem.2.bias"]), st), "onr_stem_grads_from_factors")
         else:
-            check(lib.onr_stem_bwd(
+            check(lib.onr_stem_bwd_act(
                 ptr(self.dz[0]), self.B, ptr(self.embed), self.E, ptr(self.pre1), ptr(self.h1), self.hid,
                 ptr(lin2.weight), gen.fc_dim, gen.fc_h, gen.fc_w, g0.cpi,
                 ptr(grads["stem.0.weight"]), ptr(grads["stem.0.bias"]),
-                ptr(grads["stem.2.weight"]), ptr(grads["stem.2.bias"]), ptr(self.dh1), st), "onr_stem_bwd")
+                ptr(grads["stem.2.weight"]), ptr(grads["stem.2.bias"]), ptr(self.dh1), self.act, st), "onr_stem_bwd")
             if reduce is not None:
                 reduce(self._flat_span(grads, ["stem.0.weight", "stem.0.bias", "stem.2.weight", "stem.2.bias"]))
         for ev in joins:
@@ -538,10 +558,12 @@ class NetExecutor:
         return flat[lo:hi]
 
     def scatter_block_grads(self, l, grads):
-        """dK/dbias of ERB block l -> gradients of its nine branch tensors (fold backward)."""
+        """dK/dbias of a multi-branch block l -> gradients of its branch tensors (fold backward)."""
         g, blk, st = self.geoms[l], self.gen.layers[l], _lib.stream()
         pfx = f"layers.{l}."
-        if self._fold_tc:
+        if blk.fold_kind() == "set":
+            branches.fold_bwd(self.lib, blk, self.dK[l], self.dbias[l], lambda n: grads.get(pfx + n), st)
+        elif self._fold_tc:
             names = ("rbr_3x3_branch.weight", "rbr_3x3_branch.bias", "rbr_1x3_branch.weight", "rbr_1x3_branch.bias",
                      "rbr_3x1_branch.weight", "rbr_3x1_branch.bias", "rbr_1x1_3x3_1x1_branch_1x1_1.weight",
                      "rbr_1x1_3x3_1x1_branch_3x3.weight", "rbr_1x1_3x3_1x1_branch_1x1_2.weight")

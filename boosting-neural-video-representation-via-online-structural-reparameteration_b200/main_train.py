@@ -64,6 +64,36 @@ def evaluate(model, cache, pe, args):
     return torch.cat(psnrs).mean().view(1), torch.cat(msssims).mean().view(1), n / max(t_fwd, 1e-9)
 
 
+def fit_epoch(fitter, cache, args, epoch, total_epochs, spe, world, rank, local_rank, log_path=None):
+    """One epoch of the reference step loop (main_train.py:229-267; main_eval.py:450-507 runs the same loop for
+    prune-then-finetune): frame order, `FrameFitter.step` per iteration, the reference's progress line every
+    `print_freq` steps.  Returns the epoch means [loss, L1, SSIM, MSE, PSNR, MS-SSIM] as a CPU tensor."""
+    device, B, data_size = fitter.dev, args.batchSize, len(cache)
+    order = sharding.shard_indices(data_size, world, rank, epoch, seed=args.manualSeed) if B == 1 else None
+    stats = []
+    n_steps = spe if not args.debug else min(spe, 11)
+    for i in range(n_steps):
+        if B == 1:
+            idx = torch.tensor([order[i]], device=device)
+        else:
+            perm = sharding.epoch_permutation(data_size, epoch, args.manualSeed)
+            sl = [perm[(i * world * B + rank * B + k) % data_size] for k in range(B)]
+            idx = torch.tensor(sl, device=device)
+        out = fitter.step(cache.frames[idx], cache.t[idx])
+        stats.append(out[:6].clone())
+        if i % args.print_freq == 0 or i == n_steps - 1:
+            st = torch.stack(stats).mean(0).cpu()
+            lr = fitter.opt.param_groups[0]['lr']
+            print_str = '[{}] Rank:{}, Epoch[{}/{}], Step [{}/{}], lr:{:.2e} PSNR: {}, MSSSIM: {}'.format(
+                datetime.now().strftime("%Y/%m/%d %H:%M:%S"), local_rank, epoch + 1, total_epochs, i + 1, n_steps,
+                lr, RoundTensor(st[4:5], 2, False), RoundTensor(st[5:6], 4, False))
+            print(print_str, flush=True)
+            if rank == 0 and log_path:
+                with open(log_path, 'a') as f:
+                    f.write(print_str + '\n')
+    return torch.stack(stats).mean(0).cpu()
+
+
 def train(local_rank, rank, world, args):
     torch.manual_seed(args.manualSeed)
     np.random.seed(args.manualSeed)
@@ -92,34 +122,10 @@ def train(local_rank, rank, world, args):
     spe = sharding.steps_per_epoch(data_size, world * args.batchSize)
     fitter = FrameFitter(model, pe, args, optimizer=optimizer, world_size=world, steps_per_epoch=spe,
                          data_size=data_size)
-    B = args.batchSize
-
     start = datetime.now()
     for epoch in range(args.epochs):
         epoch_start = datetime.now()
-        order = sharding.shard_indices(data_size, world, rank, epoch, seed=args.manualSeed) if B == 1 else None
-        stats = []
-        n_steps = spe if not args.debug else min(spe, 11)
-        for i in range(n_steps):
-            if B == 1:
-                idx = torch.tensor([order[i]], device=device)
-            else:
-                perm = sharding.epoch_permutation(data_size, epoch, args.manualSeed)
-                sl = [perm[(i * world * B + rank * B + k) % data_size] for k in range(B)]
-                idx = torch.tensor(sl, device=device)
-            out = fitter.step(cache.frames[idx], cache.t[idx])
-            stats.append(out[:6].clone())
-            if i % args.print_freq == 0 or i == n_steps - 1:
-                st = torch.stack(stats).mean(0).cpu()
-                lr = fitter.opt.param_groups[0]['lr']
-                print_str = '[{}] Rank:{}, Epoch[{}/{}], Step [{}/{}], lr:{:.2e} PSNR: {}, MSSSIM: {}'.format(
-                    datetime.now().strftime("%Y/%m/%d %H:%M:%S"), local_rank, epoch + 1, args.epochs, i + 1, n_steps,
-                    lr, RoundTensor(st[4:5], 2, False), RoundTensor(st[5:6], 4, False))
-                print(print_str, flush=True)
-                if rank == 0:
-                    with open(log_path, 'a') as f:
-                        f.write(print_str + '\n')
-        st = torch.stack(stats).mean(0).cpu()
+        st = fit_epoch(fitter, cache, args, epoch, args.epochs, spe, world, rank, local_rank, log_path)
         train_psnr, train_msssim = st[4:5], st[5:6]
         if rank == 0:
             h, w = fitter.H, fitter.W

@@ -7,7 +7,8 @@ Same public surface (reference model.py:303-625): `Generator(**kargs)`, `NeRVBlo
 `F.conv2d`, `nn.PixelShuffle`, `nn.SiLU`, `nn.Linear` kernel is ever dispatched — the modules are
 parameter containers and every arithmetic step runs in liborepnerv.so (sm_100a) via `engine.NetExecutor`.
 
-Scope: branch_type in {NeRV_vanilla, ERB}, act 'swish', norm 'none',
+Scope: branch_type NeRV_vanilla | ERB (the north-star path) and, folded online the same way,
+ACB | RepVGG | DBB | ECB (8f-4, branches.py); every activation of the reference's ActivationLayer; norm 'none',
 num_blocks 1, single-resolution head.  Anything else raises NotImplementedError — there is no fallback.
 """
 import ctypes as C
@@ -15,11 +16,14 @@ import ctypes as C
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, branches
 from ._lib import check, ptr
 from .engine import NetExecutor, pad32, conv_tile_n, _conv_plan, _wgrad_plan
 
-SUPPORTED_BRANCHES = ("NeRV_vanilla", "ERB")
+SUPPORTED_BRANCHES = ("NeRV_vanilla", "ERB") + branches.FOLDED_BRANCH_TYPES
+# reference model.py:86-117 (ActivationLayer) -> activation code of the kernels (csrc/act.cuh)
+ACT_CODES = {"swish": 0, "relu": 1, "leaky": 2, "leaky01": 3, "relu6": 4, "gelu": 5, "softplus": 6, "hardswish": 7,
+             "sin": 8}
 _ERB_BRANCHES = ("rbr_3x3_branch", "rbr_3x1_branch", "rbr_1x3_branch", "rbr_1x1_3x3_1x1_branch_1x1_1",
                  "rbr_1x1_3x3_1x1_branch_3x3", "rbr_1x1_3x3_1x1_branch_1x1_2")
 
@@ -27,8 +31,8 @@ _ERB_BRANCHES = ("rbr_3x3_branch", "rbr_3x1_branch", "rbr_1x3_branch", "rbr_1x1_
 def _require(cond, what):
     if not cond:
         raise NotImplementedError(
-            f"{what} is outside the B200 hot path (supported: branch_type NeRV_vanilla|ERB, act swish, "
-            "norm none, num_blocks 1, single_res); no fallback path exists")
+            f"{what} is outside the B200 hot path (supported: branch_type NeRV_vanilla|ERB|ACB|RepVGG|DBB|ECB, act "
+            f"{'|'.join(ACT_CODES)}, norm none, num_blocks 1, single_res); no fallback path exists")
 
 
 def _fire_prune_hooks(conv):
@@ -73,12 +77,38 @@ class _FoldFunction(torch.autograd.Function):
         return (None,) + tuple(grads)
 
 
+class _BranchSetFoldFunction(torch.autograd.Function):
+    """Online fold of an ACB / RepVGG / DBB / ECB branch set into one 3x3 kernel + bias (csrc/fold_branches.cu; the
+    reference runs model.py:541-565 un-folded) with its analytic backward.  `tensors` follow branches.branch_slots."""
+
+    @staticmethod
+    def forward(ctx, blk, *tensors):
+        lib, st = _lib.lib(), _lib.stream()
+        dev = tensors[0].device
+        K = torch.empty(blk.out_channels, blk.ngf, 3, 3, dtype=torch.float32, device=dev)
+        bias = torch.empty(blk.out_channels, dtype=torch.float32, device=dev)
+        branches.fold_fwd(lib, blk, K, bias, st)
+        ctx.blk = blk
+        return K, bias
+
+    @staticmethod
+    def backward(ctx, dK, dbias):
+        lib, st = _lib.lib(), _lib.stream()
+        blk = ctx.blk
+        dK = dK.contiguous()
+        dbias = dbias.contiguous() if dbias is not None else torch.zeros(blk.out_channels, device=dK.device)
+        slots = branches.branch_slots(blk)
+        grads = {name: (torch.zeros_like(t) if t.requires_grad else None) for _, name, t in slots}
+        branches.fold_bwd(lib, blk, dK, dbias, grads.get, st)
+        return (None,) + tuple(grads[name] for _, name, _ in slots)
+
+
 class _BlockFunction(torch.autograd.Function):
     """conv3x3 + PixelShuffle + SiLU of ONE block on NCHW fp32 tensors (module-boundary path used when a
     NeRVBlock is called on its own; the Generator uses the fused executor instead)."""
 
     @staticmethod
-    def forward(ctx, x, K, bias, stride, cnew):
+    def forward(ctx, x, K, bias, stride, cnew, act=0):
         lib = _lib.lib()
         st = _lib.stream()
         B, cin, H, W = x.shape
@@ -101,10 +131,12 @@ class _BlockFunction(torch.autograd.Function):
                                    npad, cpi_rows, ptr(wf), ptr(wd), ptr(bias_p), st), "onr_pack_weights")
         y = torch.empty(B, H * s, W * s, cpo, dtype=bf16, device=dev)
         d = torch.empty_like(y)
-        plan = _conv_plan(lib, kind=_lib.CONV_FPROP_TRAIN, B=B, H=H, W=W, a=ptr(xh), a_cp=cpi, a_s=1,
-                          w=ptr(wf), n_rows=npad, n_total=nk, out=ptr(y), out_cp=cpo, out_s=s, out_d=ptr(d),
-                          bias_p=ptr(bias_p), dmul=None)
+        plan = _conv_plan(lib, kind=_lib.CONV_FPROP_TRAIN if act == 0 else _lib.CONV_FPROP_Z, B=B, H=H, W=W,
+                          a=ptr(xh), a_cp=cpi, a_s=1, w=ptr(wf), n_rows=npad, n_total=nk, out=ptr(y), out_cp=cpo,
+                          out_s=s, out_d=ptr(d) if act == 0 else None, bias_p=ptr(bias_p), dmul=None)
         check(lib.onr_conv_plan_run(plan.handle, st), "onr_conv_plan_run")
+        if act != 0:
+            check(lib.onr_act_map(ptr(y), ptr(d), B * H * s * W * s, cnew, cpo, act, st), "onr_act_map")
         out = torch.empty(B, cnew, H * s, W * s, dtype=torch.float32, device=dev)
         check(lib.onr_nhwc_bf16_to_nchw(ptr(y), B, cnew, H * s, W * s, cpo, ptr(out), st), "to_nchw")
         ctx.geom = (B, cin, H, W, s, cnew, cpi, cpo, nk, cpi_rows)
@@ -138,7 +170,18 @@ class _BlockFunction(torch.autograd.Function):
         dx = torch.empty(B, cin, H, W, dtype=torch.float32, device=dev)
         check(lib.onr_nhwc_bf16_to_nchw(ptr(dxh), B, cin, H, W, cpi, ptr(dx), st), "to_nchw")
         torch.cuda.current_stream().synchronize()     # plans (TMA descriptors) must outlive the launches
-        return dx, dK, db, None, None
+        return dx, dK, db, None, None, None
+
+
+def activation_module(act_type):
+    """reference model.py:86-117 (ActivationLayer) — kept for module traversal / print(model); never called."""
+    table = {'relu': lambda: nn.ReLU(True), 'leaky': lambda: nn.LeakyReLU(inplace=True),
+             'leaky01': lambda: nn.LeakyReLU(negative_slope=0.1, inplace=True), 'relu6': lambda: nn.ReLU6(inplace=True),
+             'gelu': nn.GELU, 'swish': lambda: nn.SiLU(inplace=True), 'softplus': nn.Softplus,
+             'hardswish': lambda: nn.Hardswish(inplace=True), 'sin': lambda: torch.sin}
+    if act_type not in table:
+        raise KeyError(f"Unknown activation function {act_type}.")
+    return table[act_type]()
 
 
 class NeRVBlock(nn.Module):
@@ -151,11 +194,12 @@ class NeRVBlock(nn.Module):
         self.branch_type = kargs['branch_type']
         _require(self.branch_type in SUPPORTED_BRANCHES, f"branch_type {self.branch_type!r}")
         _require(kargs.get('norm', 'none') == 'none', f"norm {kargs.get('norm')!r}")
-        _require(kargs.get('act', 'swish') == 'swish', f"act {kargs.get('act')!r}")
+        self.act_name = kargs.get('act', 'swish')
+        _require(self.act_name in ACT_CODES, f"act {self.act_name!r}")
         # parameter-free modules kept so that print(model) / module traversal look like the reference
         self.up_scale = nn.PixelShuffle(self.stride)
         self.norm = nn.Identity()
-        self.act = nn.SiLU(inplace=True)
+        self.act = activation_module(self.act_name)
         self.out_channels = self.new_ngf * self.stride * self.stride
         ci, co = self.ngf, self.out_channels
         if self.deploy:
@@ -163,6 +207,8 @@ class NeRVBlock(nn.Module):
         elif self.branch_type == "NeRV_vanilla":
             self.branch = nn.Conv2d(ci, co, (3, 3), 1, 1, bias=kargs.get('bias', True))
             _require(self.branch.bias is not None, "bias=False")
+        elif self.branch_type in branches.FOLDED_BRANCH_TYPES:
+            branches.create_branches(self, self.branch_type, ci, co)
         else:  # ERB: creation order matches reference model.py:324-343 (same RNG consumption)
             self.rbr_3x3_branch = nn.Conv2d(ci, co, (3, 3), 1, 1)
             self.rbr_3x1_branch = nn.Conv2d(ci, co, (3, 1), 1, (1, 0))
@@ -174,6 +220,19 @@ class NeRVBlock(nn.Module):
     # ---- structure queries used by the executor -------------------------------------------------
     def is_erb_train(self):
         return (not self.deploy) and self.branch_type == "ERB" and hasattr(self, "rbr_3x3_branch")
+
+    def fold_kind(self):
+        """'erb' (tensor-core fold, fold_tc.cu), 'set' (ACB / RepVGG / DBB / ECB, fold_branches.cu) or None (a single
+        convolution: vanilla or deploy state)."""
+        if self.is_erb_train():
+            return "erb"
+        if (not self.deploy) and self.branch_type in branches.FOLDED_BRANCH_TYPES and hasattr(self, "rbr_3x3_branch"):
+            return "set"
+        return None
+
+    @property
+    def act_code(self):
+        return ACT_CODES[self.act_name]
 
     def fold_plan(self):
         """Tensor-core fold plan of this block (created on first use; holds the fold's workspace on the device)."""
@@ -206,8 +265,12 @@ class NeRVBlock(nn.Module):
     # ---- reference API -----------------------------------------------------------------------
     def get_equivalent_kernel_bias(self):
         """Reference model.py:450-478; differentiable w.r.t. the nine branch tensors."""
-        if not self.is_erb_train():
-            raise AttributeError("get_equivalent_kernel_bias needs the ERB training branches")
+        kind = self.fold_kind()
+        if kind == "set":
+            # the reference has no fold for these sets (AttributeError, SURVEY.md 2.1 row 5); here they fold like ERB
+            return _BranchSetFoldFunction.apply(self, *[t for _, _, t in branches.branch_slots(self)])
+        if kind is None:
+            raise AttributeError("get_equivalent_kernel_bias needs the training branches")
         b = self
         return _FoldFunction.apply(
             self, b.rbr_3x3_branch.weight, b.rbr_3x3_branch.bias, b.rbr_1x3_branch.weight, b.rbr_1x3_branch.bias,
@@ -226,7 +289,7 @@ class NeRVBlock(nn.Module):
             self.rbr_reparam = nn.Conv2d(self.ngf, self.out_channels, (3, 3), 1, 1, bias=True)
         self.rbr_reparam.weight.data = kernel
         self.rbr_reparam.bias.data = bias
-        for name in _ERB_BRANCHES + ("branch",):
+        for name in _ERB_BRANCHES + ("branch",) + branches.SET_BRANCH_MODULES:
             if hasattr(self, name):
                 self.__delattr__(name)
         self.__dict__.pop("_fold_plan_obj", None)
@@ -234,12 +297,24 @@ class NeRVBlock(nn.Module):
 
     def forward(self, x):
         """Reference model.py:518-567 on NCHW fp32 tensors (module-boundary path)."""
-        if self.is_erb_train():
+        if self.fold_kind() is not None:
             K, b = self.get_equivalent_kernel_bias()
         else:
             conv = self.single_conv()
             K, b = conv.weight, conv.bias
-        return _BlockFunction.apply(x, K, b, self.stride, self.new_ngf)
+        return _BlockFunction.apply(x, K, b, self.stride, self.new_ngf, self.act_code)
+
+
+class _FnModule(nn.Module):
+    """nn.Sequential slot for a bare function (the reference puts torch.sin itself into the stem's Sequential, which
+    torch >= 1.9 rejects; the index layout stem.0 / stem.2 is what matters for the state dict)."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, x):
+        return self.fn(x)
 
 
 class _GeneratorFunction(torch.autograd.Function):
@@ -264,14 +339,16 @@ class _GeneratorFunction(torch.autograd.Function):
         named = list(gen.named_parameters())
         pg = gen.persistent_grads()
         owned = [p.grad is pg[n] for n, p in named]
-        fast = all(p.requires_grad and (p.grad is None or o) for (n, p), o in zip(named, owned))
+        # (SeqConv3x3.mask is a Parameter that never requires a gradient: it takes no part in the binding)
+        fast = all((not p.requires_grad) or p.grad is None or o for (n, p), o in zip(named, owned))
         if fast and (gen._grads_clean or not any(owned)):
             if not gen._grads_clean:
                 pg["__flat__"].zero_()
             ex.backward(gimg.contiguous(), pg)
             gen._grads_clean = False
             for n, p in named:
-                p.grad = pg[n]
+                if p.requires_grad:
+                    p.grad = pg[n]
             return (None, None, None) + (None,) * len(named)
         grads = gen.alloc_grads()
         ex.backward(gimg.contiguous(), grads)
@@ -287,12 +364,15 @@ class Generator(nn.Module):
         stem_dim, stem_num = [int(x) for x in kargs['stem_dim_num'].split('_')]
         self.fc_h, self.fc_w, self.fc_dim = [int(x) for x in kargs['fc_hw_dim'].split('_')]
         _require(stem_num == 1, f"stem_dim_num with {stem_num} hidden layers")
-        _require(kargs.get('act', 'swish') == 'swish', f"act {kargs.get('act')!r}")
+        self.act_name = kargs.get('act', 'swish')
+        _require(self.act_name in ACT_CODES, f"act {self.act_name!r}")
         _require(kargs.get('num_blocks', 1) == 1, "num_blocks > 1")
         _require(bool(kargs.get('sin_res', True)), "multi-resolution heads (sin_res=False)")
         _require(kargs.get('bias', True), "bias=False")
         # reference MLP(): Linear, act, Linear, act with one shared activation module (model.py:184-188)
-        act_fn = nn.SiLU(inplace=True)
+        act_fn = activation_module(self.act_name)
+        if not isinstance(act_fn, nn.Module):          # 'sin' is the bare torch.sin in the reference (model.py:104)
+            act_fn = _FnModule(act_fn)
         self.stem = nn.Sequential(nn.Linear(kargs['embed_length'], stem_dim), act_fn,
                                   nn.Linear(stem_dim, self.fc_h * self.fc_w * self.fc_dim), act_fn)
         self.layers, self.head_layers = [nn.ModuleList() for _ in range(2)]
@@ -316,6 +396,10 @@ class Generator(nn.Module):
         self._grads_clean = False
 
     # ---- helpers for the executor ---------------------------------------------------------------
+    @property
+    def act_code(self):
+        return ACT_CODES[self.act_name]
+
     def head_name(self):
         return f"head_layers.{len(self.layers) - 1}"
 

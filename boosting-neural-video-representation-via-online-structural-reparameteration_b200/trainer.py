@@ -52,7 +52,13 @@ class _Exchange:
 
 class FrameFitter:
     def __init__(self, model, pe, args, optimizer=None, world_size=1, steps_per_epoch=None, data_size=None,
-                 use_graph=True, with_msssim=True):
+                 use_graph=True, with_msssim=True, grad_masks=None, epoch_offset=0, epoch_mod=None):
+        """grad_masks (prune-then-finetune, reference main_eval.py:213-545): dict parameter name -> fp32 mask of the
+        parameter's shape.  Every step the gradients are multiplied by the masks before Adam — the gradient of prune's
+        `weight = weight_orig * weight_mask` — so a masked entry (zero gradient from the first step on a fresh
+        optimizer) never moves; an all-zero mask freezes a tensor.
+        epoch_offset / epoch_mod: the LR schedule is evaluated at epoch (epoch_offset + step // steps_per_epoch) %
+        epoch_mod (default: args.epochs) while the Adam step count starts at 1 (main_eval.py:446-466)."""
         self.lib = _lib.lib()
         self.model, self.pe, self.args = model, pe, args
         self.world = world_size
@@ -69,7 +75,8 @@ class FrameFitter:
         self.grads = model.alloc_grads()
         self.flat_grad = self.grads["__flat__"]
         for n, p in model.named_parameters():
-            p.grad = self.grads[n]
+            if p.requires_grad:                       # SeqConv3x3.mask (ECB) is a constant Parameter
+                p.grad = self.grads[n]
         self.opt = optimizer if optimizer is not None else FusedAdam(model.parameters(), lr=args.lr,
                                                                       betas=(args.beta, 0.999))
         if not isinstance(self.opt, FusedAdam):
@@ -109,6 +116,20 @@ class FrameFitter:
         in_blocks = {id(p) for ps in self._block_params for p in ps}
         self._rest_params = [p for _, p in named if id(p) not in in_blocks]
         self.adam_early = [l for l in self.adam_early if 0 <= l < self.ex.L]
+        self.epoch_offset = int(epoch_offset)
+        self.epoch_mod = int(epoch_mod) if epoch_mod is not None else int(args.epochs)
+        self.grad_mask = None
+        if grad_masks:
+            # one flat mask beside the flat gradient buffer (ones outside the masked tensors): ONE launch per step
+            self.grad_mask = torch.ones_like(self.flat_grad)
+            offs = self.grads["__offsets__"]
+            for n, m in grad_masks.items():
+                o, k = offs[n]
+                if m.numel() != k:
+                    raise ValueError(f"grad mask of {n} has {m.numel()} elements, the parameter {k}")
+                self.grad_mask[o:o + k] = m.reshape(-1).to(self.dev, torch.float32)
+            # the masks apply to the complete gradients, right before the one Adam launch at the end of the step
+            self.fold_ahead, self.adam_early = False, []
         early_ids = {id(p) for l in self.adam_early for p in self._block_params[l]}
         self._late_params = [p for _, p in named if id(p) not in early_ids]
         self._weights_valid = False
@@ -183,9 +204,9 @@ class FrameFitter:
     def _tick(self):
         lr_dev, step_dev = self.opt.device_scalars(self.dev)
         a = self.args
-        check(self.lib.onr_sched_tick(ptr(step_dev), ptr(lr_dev), float(a.lr), self.steps_per_epoch, self.data_size,
-                                      int(a.warmup), int(a.epochs), 0 if a.lr_type == 'cosine' else 1, _lib.stream()),
-              "onr_sched_tick")
+        check(self.lib.onr_sched_tick_ex(ptr(step_dev), ptr(lr_dev), float(a.lr), self.steps_per_epoch, self.data_size,
+                                         int(a.warmup), int(a.epochs), 0 if a.lr_type == 'cosine' else 1,
+                                         self.epoch_offset, self.epoch_mod, _lib.stream()), "onr_sched_tick_ex")
 
     def _body_post(self):
         """LR schedule tick + fused Adam (+ gradient averaging and zeroing); with fold-ahead only the tensors outside
@@ -200,6 +221,9 @@ class FrameFitter:
             return
         if self.device_sched:
             self._tick()
+        if self.grad_mask is not None:
+            check(self.lib.onr_mul_inplace_f32(ptr(self.flat_grad), ptr(self.grad_mask), self.flat_grad.numel(),
+                                               _lib.stream()), "onr_mul_inplace_f32")
         self.opt.step(device_schedule=self.device_sched)
 
     def release_graph(self):
@@ -218,7 +242,7 @@ class FrameFitter:
 
     def _host_lr(self):
         t = self.host_step
-        epoch = (t // self.steps_per_epoch) % self.args.epochs
+        epoch = (self.epoch_offset + t // self.steps_per_epoch) % self.epoch_mod
         it = t % self.steps_per_epoch
         lr = self.args.lr * lr_multiplier(epoch, it, self.data_size, self.args)
         for g in self.opt.param_groups:

@@ -50,6 +50,13 @@ int onr_pe_stem_fwd(const float* t_norm, int B, const float* freqs /* [levels] =
                     const float* W2, const float* b2, int fc_dim, int fh, int fw, int Cp,
                     float* embed, float* pre1, float* h1,
                     void* x0_bf16, void* dstem_bf16, void* stream);
+/* The same with the stem's activation given as a code (see onr_act_map): model.py:184-188 builds the MLP with the
+ * --act of the run.  onr_pe_stem_fwd == act 0 (swish). */
+int onr_pe_stem_fwd_act(const float* t_norm, int B, const float* freqs, int levels,
+                        const float* W1, const float* b1, int hid,
+                        const float* W2, const float* b2, int fc_dim, int fh, int fw, int Cp,
+                        float* embed, float* pre1, float* h1,
+                        void* x0_bf16, void* dstem_bf16, int act, void* stream);
 /* utils.py:121-129 alone: embed[B,2L] from t_norm[B] (what PositionalEncoding.forward returns). */
 int onr_pos_encoding(const float* t_norm, int B, const float* freqs, int levels, float* embed, void* stream);
 /* Backward of the stem (autograd of model.py:612 through main_train.py:249).
@@ -60,6 +67,11 @@ int onr_stem_bwd(const void* g0_bf16, int B, const float* embed, int emb_len,
                  const float* W2, int fc_dim, int fh, int fw, int Cp,
                  float* gW1, float* gb1, float* gW2, float* gb2,
                  float* scratch_dh1 /* [B,hid] */, void* stream);
+int onr_stem_bwd_act(const void* g0_bf16, int B, const float* embed, int emb_len,
+                     const float* pre1, const float* h1, int hid,
+                     const float* W2, int fc_dim, int fh, int fw, int Cp,
+                     float* gW1, float* gb1, float* gW2, float* gb2,
+                     float* scratch_dh1 /* [B,hid] */, int act, void* stream);
 
 /* Data-parallel form of the stem backward (batch 1 per rank): the stem gradients of one frame are rank-1, so ranks
  * exchange the FACTORS (onr_stem_factor_floats() fp32 per rank: g | h1 | dpre1 | embed) with an all-gather instead of
@@ -69,6 +81,9 @@ size_t onr_stem_factor_floats(int fc_dim, int fh, int fw, int hid, int emb_len);
 int onr_stem_bwd_factors(const void* g0_bf16, const float* embed, int emb_len, const float* pre1, const float* h1,
                          int hid, const float* W2, int fc_dim, int fh, int fw, int Cp,
                          float* slot /* this rank's slot */, float* scratch_dh1 /* [hid] */, void* stream);
+int onr_stem_bwd_factors_act(const void* g0_bf16, const float* embed, int emb_len, const float* pre1, const float* h1,
+                             int hid, const float* W2, int fc_dim, int fh, int fw, int Cp,
+                             float* slot, float* scratch_dh1, int act, void* stream);
 int onr_stem_grads_from_factors(const float* slots /* [K][onr_stem_factor_floats()] */, int K, int emb_len, int hid,
                                 int fc_dim, int fh, int fw, float* gW1, float* gb1, float* gW2, float* gb2,
                                 void* stream);
@@ -107,6 +122,27 @@ int onr_fold_plan_fwd(onr_fold_plan* plan, const float* w3x3, const float* b3x3,
 int onr_fold_plan_bwd(onr_fold_plan* plan, const float* dKt, const float* dbias,
                       float* g3x3, float* gb3x3, float* g1x3, float* gb1x3, float* g3x1, float* gb3x1,
                       float* gw1, float* gw2, float* gw3, void* stream);
+/* ------------------------------------------------------------------ the other linear branch sets
+ * model.py:345-393 (ACB, RepVGG, DBB, ECB; SeqConv3x3 :191-300).  The reference runs them as an explicit multi-branch
+ * forward (:541-565) and has no fold for them; every branch is linear, so their sum is ONE 3x3 convolution.  The fold
+ * below builds that kernel on the device every step (fp32), the block then runs the same tcgen05 convolution as ERB,
+ * and the backward scatters dK / dbias to the branch parameters.  Unused branches are NULL.  All tensors in the
+ * reference's layouts: w3x3[Cout,Cin,3,3], w1x3[Cout,Cin,1,3], w3x1[Cout,Cin,3,1], w1x1[Cout,Cin,1,1] (+ biases [Cout]);
+ * seq_w1[2Cin,Cin,1,1] -> seq_w2[Cout,2Cin,3,3] (the 1x1 -> 3x3 branch, no biases); avg_w[Cout,Cin,1,1] (1x1 ->
+ * AvgPool2d(3,1,1)); edge_*[e] = SeqConv3x3 e (sobel-x, sobel-y, laplacian): k0[Cout,Cin,1,1], b0[Cout],
+ * scale[Cout,1,1,1], bias[Cout], mask[Cout,1,3,3] (mask is a constant: it never receives a gradient). */
+typedef struct onr_branch_set {
+    int cin, cout;
+    float *w3x3, *b3x3, *w1x3, *b1x3, *w3x1, *b3x1, *w1x1, *b1x1;
+    float *seq_w1, *seq_w2, *avg_w;
+    float *edge_k0[3], *edge_b0[3], *edge_scale[3], *edge_bias[3], *edge_mask[3];
+} onr_branch_set;
+/* K[Cout,Cin,3,3], bias[Cout] (OVERWRITTEN) = the single-convolution equivalent of the branch set. */
+int onr_branch_fold_fwd(const onr_branch_set* w, float* K, float* bias, void* stream);
+/* g holds the gradient pointers in the same slots (NULL: not wanted); every present gradient is OVERWRITTEN. */
+int onr_branch_fold_bwd(const onr_branch_set* w, const float* dK, const float* dbias, const onr_branch_set* g,
+                        void* stream);
+
 /* Kt[Cout][9][Cin] <-> K[Cout][Cin][3][3] (to_oihw != 0: tap-major -> reference layout). */
 int onr_tapmajor_permute(const float* src, float* dst, int Cin, int Cout, int to_oihw, void* stream);
 /* onr_pack_weights / onr_unpack_wgrad for tap-major kernels. */
@@ -195,6 +231,13 @@ void onr_wgrad_plan_destroy(onr_wgrad_plan* plan);
 int onr_nchw_to_nhwc_bf16(const float* src, int B, int C, int H, int W, int Cp, void* dst, void* stream);
 int onr_nhwc_bf16_to_nchw(const void* src, int B, int C, int H, int W, int Cp, float* dst, void* stream);
 
+/* ------------------------------------------------------------------ A5 for the other activations (8f-4)
+ * model.py:86-117 (ActivationLayer) + :567.  Activation codes: 0 swish, 1 relu, 2 leaky (0.01), 3 leaky01 (0.1),
+ * 4 relu6, 5 gelu (erf), 6 softplus, 7 hardswish, 8 sin.  swish is fused into the convolution epilogue
+ * (ONR_CONV_FPROP_TRAIN / _INFER); for the others the block runs in ONR_CONV_FPROP_Z mode (pre-activation z) and this
+ * kernel turns z[pixels][Cp] (NHWC bf16) into y = act(z) IN PLACE and d = act'(z) (d may be NULL: decode). */
+int onr_act_map(void* zy_bf16, void* d_bf16, size_t pixels, int C, int Cp, int act, void* stream);
+
 /* ------------------------------------------------------------------ A6: RGB head
  * model.py:601, :620-623: 1x1 conv C->3 + bias, then (tanh+1)/2 or sigmoid.
  * y NHWC bf16 [B][H][W][Cp] -> img NCHW fp32 [B][3][H][W]. */
@@ -262,6 +305,11 @@ int onr_adam_multi(const uint64_t* table, int n_tensors, size_t total_blocks,
  * cur_epoch = epoch + iter/data_size.  lr_type 0 = cosine, 1 = const; warm-up 0.1 -> 1 over `warmup` epochs. */
 int onr_sched_tick(int* step_dev, float* lr_dev, double lr0, int steps_per_epoch, int data_size,
                    int warmup, int epochs, int lr_type, void* stream);
+/* The same tick for the prune-then-finetune loop (main_eval.py:446-466): the optimizer restarts (step count from 1)
+ * while the epoch numbering continues at the checkpoint's epoch; adjust_lr is evaluated at
+ * (epoch_offset + step / steps_per_epoch) % epoch_mod against the original --epochs / warm-up. */
+int onr_sched_tick_ex(int* step_dev, float* lr_dev, double lr0, int steps_per_epoch, int data_size,
+                      int warmup, int epochs, int lr_type, int epoch_offset, int epoch_mod, void* stream);
 
 /* ------------------------------------------------------------------ A12/A13: eval-side weight transforms
  * main_eval.py:572-587 (prune.global_unstructured, L1Unstructured): the global k-th smallest |w| is found
@@ -272,6 +320,9 @@ int onr_abs_radix_hist(const float* w, size_t n, uint32_t prefix, uint32_t prefi
                        unsigned long long* hist256, void* stream);
 /* mask[i] = |w[i]| > thr ? 1 : 0 (fp32, like torch's weight_mask); w_out = w * mask. Either may be NULL. */
 int onr_apply_magnitude_mask(const float* w, size_t n, float thr, float* mask, float* w_out, void* stream);
+/* g[i] *= m[i] over n floats (both 16-byte aligned): the gradient side of prune's weight = weight_orig * weight_mask
+ * (main_eval.py:213-545, prune-then-finetune; torch.nn.utils.prune's forward-pre-hook + autograd in the reference). */
+int onr_mul_inplace_f32(float* g, const float* m, size_t n, void* stream);
 /* utils.py:11-67 quantize_per_tensor with axis 0 over rows of a [rows, cols] view (axis -1: rows=1):
  * min/max over non-zero entries, scale=(max-min)/2^bit, q=round((t-min)/(scale+1e-19)),
  * new=min+scale*q.  q_out and new_out may alias nothing; either may be NULL. */

@@ -40,10 +40,10 @@ def silu(x):
     return x * torch.sigmoid(x)
 
 
-def stem_forward(embed, W1, b1, W2, b2, fc_dim, fc_h, fc_w):
-    """reference model.py:174-188 (MLP: Linear, SiLU, Linear, SiLU) and :612-613 (view to NCHW)."""
-    h = silu(F.linear(embed, W1, b1))
-    o = silu(F.linear(h, W2, b2))
+def stem_forward(embed, W1, b1, W2, b2, fc_dim, fc_h, fc_w, act='swish'):
+    """reference model.py:174-188 (MLP: Linear, act, Linear, act) and :612-613 (view to NCHW)."""
+    h = activation(F.linear(embed, W1, b1), act)
+    o = activation(F.linear(h, W2, b2), act)
     return o.view(o.size(0), fc_dim, fc_h, fc_w)
 
 
@@ -78,10 +78,81 @@ def erb_fold_backward(dK, db, w1, w2, w3):
     return g
 
 
+# ----------------------------------------------------------------------------- 8f-4: the other linear branch sets
+def seqconv3x3_forward(x, k0, b0, scale, bias, mask):
+    """reference model.py:277-289 (SeqConv3x3.forward): 1x1 conv with bias, border padded WITH that bias, depthwise
+    3x3 with kernel scale*mask and bias."""
+    y0 = F.conv2d(x, k0, b0)
+    y0 = F.pad(y0, (1, 1, 1, 1), 'constant', 0)
+    b0p = b0.view(1, -1, 1, 1)
+    frame = torch.ones_like(y0)
+    frame[:, :, 1:-1, 1:-1] = 0
+    y0 = y0 * (1 - frame) + b0p * frame
+    return F.conv2d(y0, scale * mask, bias, groups=k0.shape[0])
+
+
+def branch_set_forward(x, sd, p, branch_type):
+    """reference model.py:541-565: the EXPLICIT multi-branch forward of ACB / RepVGG / DBB / ECB (pre-PixelShuffle)."""
+    c = lambda n, pad: F.conv2d(x, sd[p + n + '.weight'], sd.get(p + n + '.bias'), padding=pad)     # noqa: E731
+    if branch_type == 'ACB':
+        return c('rbr_3x3_branch', 1) + c('rbr_3x1_branch', (1, 0)) + c('rbr_1x3_branch', (0, 1))
+    if branch_type == 'RepVGG':
+        return c('rbr_3x3_branch', 1) + c('rbr_1x1_branch', 0)
+    seq = F.conv2d(F.conv2d(x, sd[p + 'rbr_1x1_3x3_branch_1x1.weight']), sd[p + 'rbr_1x1_3x3_branch_3x3.weight'],
+                   padding=1)
+    if branch_type == 'DBB':
+        avg = F.avg_pool2d(F.conv2d(x, sd[p + 'rbr_1x1_avg_branch_1x1.weight']), 3, 1, 1)
+        return c('rbr_3x3_branch', 1) + c('rbr_1x1_branch', 0) + seq + avg
+    if branch_type == 'ECB':
+        out = c('rbr_3x3_branch', 1) + seq
+        for e in EDGE_BRANCHES:
+            q = p + e + '.'
+            out = out + seqconv3x3_forward(x, sd[q + 'k0'], sd[q + 'b0'], sd[q + 'scale'], sd[q + 'bias'], sd[q + 'mask'])
+        return out
+    raise KeyError(branch_type)
+
+
+EDGE_BRANCHES = ('rbr_conv1x1_sbx_branch', 'rbr_conv1x1_sby_branch', 'rbr_conv1x1_lpl_branch')
+
+
+def branch_set_fold(sd, p):
+    """The single 3x3 kernel + bias equal to `branch_set_forward` (every branch is linear; the reference itself has no
+    fold for these sets — for SeqConv3x3 it is the closed form of its rep_params, model.py:291-300).  The branch set is
+    recognised from the keys present under prefix `p`."""
+    K, b = sd[p + 'rbr_3x3_branch.weight'], sd[p + 'rbr_3x3_branch.bias']
+    if p + 'rbr_3x1_branch.weight' in sd:                                   # ACB
+        K = K + F.pad(sd[p + 'rbr_1x3_branch.weight'], (0, 0, 1, 1)) + F.pad(sd[p + 'rbr_3x1_branch.weight'], (1, 1, 0, 0))
+        b = b + sd[p + 'rbr_1x3_branch.bias'] + sd[p + 'rbr_3x1_branch.bias']
+    if p + 'rbr_1x1_branch.weight' in sd:                                   # RepVGG, DBB
+        K = K + F.pad(sd[p + 'rbr_1x1_branch.weight'], (1, 1, 1, 1))
+        b = b + sd[p + 'rbr_1x1_branch.bias']
+    if p + 'rbr_1x1_3x3_branch_1x1.weight' in sd:                           # DBB, ECB
+        K = K + torch.einsum('omhw,mi->oihw', sd[p + 'rbr_1x1_3x3_branch_3x3.weight'],
+                             sd[p + 'rbr_1x1_3x3_branch_1x1.weight'][:, :, 0, 0])
+    if p + 'rbr_1x1_avg_branch_1x1.weight' in sd:                           # DBB
+        K = K + (sd[p + 'rbr_1x1_avg_branch_1x1.weight'] / 9).expand(-1, -1, 3, 3)
+    for e in EDGE_BRANCHES:                                                 # ECB
+        q = p + e + '.'
+        if q + 'k0' in sd:
+            dw = sd[q + 'scale'] * sd[q + 'mask']                           # [Cout,1,3,3]
+            K = K + dw * sd[q + 'k0']
+            b = b + sd[q + 'b0'] * dw.sum((1, 2, 3)) + sd[q + 'bias']
+    return K, b
+
+
 # ----------------------------------------------------------------------------- A4-A6 block / head / generator
-def block_forward(x, K, b, stride):
-    """reference model.py:539 (F.conv2d 3x3 pad 1) and :567 (PixelShuffle -> Identity -> SiLU)."""
-    return silu(F.pixel_shuffle(F.conv2d(x, K, b, stride=1, padding=1), stride))
+def activation(x, act='swish'):
+    """reference model.py:86-117 (ActivationLayer)."""
+    if act == 'swish':
+        return silu(x)
+    return {'relu': F.relu, 'leaky': lambda v: F.leaky_relu(v, 0.01), 'leaky01': lambda v: F.leaky_relu(v, 0.1),
+            'relu6': F.relu6, 'gelu': F.gelu, 'sin': torch.sin, 'softplus': F.softplus,
+            'hardswish': F.hardswish}[act](x)
+
+
+def block_forward(x, K, b, stride, act='swish'):
+    """reference model.py:539 (F.conv2d 3x3 pad 1) and :567 (PixelShuffle -> Identity -> activation)."""
+    return activation(F.pixel_shuffle(F.conv2d(x, K, b, stride=1, padding=1), stride), act)
 
 
 def head_forward(x, Wh, bh, sigmoid=False):
@@ -98,6 +169,8 @@ def block_kernel(sd, prefix):
     if prefix + 'branch.weight' in sd:
         return sd[prefix + 'branch.weight'], sd[prefix + 'branch.bias']
     p = prefix
+    if p + 'rbr_1x1_3x3_1x1_branch_1x1_1.weight' not in sd:
+        return branch_set_fold(sd, p)                                       # ACB / RepVGG / DBB / ECB
     return erb_fold(sd[p + 'rbr_3x3_branch.weight'], sd[p + 'rbr_3x3_branch.bias'],
                     sd[p + 'rbr_1x3_branch.weight'], sd[p + 'rbr_1x3_branch.bias'],
                     sd[p + 'rbr_3x1_branch.weight'], sd[p + 'rbr_3x1_branch.bias'],
@@ -108,12 +181,13 @@ def block_kernel(sd, prefix):
 def generator_forward(sd, embed, cfg, return_features=False):
     """reference model.py:611-625 for the single-resolution configuration.
     cfg: dict(fc_h, fc_w, fc_dim, strides, sigmoid)."""
+    act = cfg.get('act', 'swish')
     x = stem_forward(embed, sd['stem.0.weight'], sd['stem.0.bias'], sd['stem.2.weight'], sd['stem.2.bias'],
-                     cfg['fc_dim'], cfg['fc_h'], cfg['fc_w'])
+                     cfg['fc_dim'], cfg['fc_h'], cfg['fc_w'], act)
     feats = [x]
     for i, s in enumerate(cfg['strides']):
         K, b = block_kernel(sd, f'layers.{i}.')
-        x = block_forward(x, K, b, s)
+        x = block_forward(x, K, b, s, act)
         feats.append(x)
     last = len(cfg['strides']) - 1
     img = head_forward(x, sd[f'head_layers.{last}.weight'], sd[f'head_layers.{last}.bias'], cfg.get('sigmoid', False))
@@ -279,10 +353,13 @@ def train_step(sd, opt_state, embed, target, cfg, lr, t, loss_type='Fusion6', be
     """One iteration of reference main_train.py:238-250 on a state dict (dict name -> tensor):
     forward, Fusion loss, backward (autograd through the restated forward), Adam.  Returns
     (new_sd, new_opt_state, loss, img, grads)."""
-    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    # SeqConv3x3.mask is an nn.Parameter with requires_grad=False (model.py:222): a constant of the model
+    params = {k: (v.detach().clone() if k.endswith('.mask') else v.detach().clone().requires_grad_(True))
+              for k, v in sd.items()}
     img = generator_forward(params, embed, cfg)
     loss = loss_fn(img, target, loss_type)
-    names = list(params)
+    names = [k for k in params if params[k].requires_grad]
+    const = {k: params[k] for k in params if not params[k].requires_grad}
     grads = torch.autograd.grad(loss, [params[n] for n in names], allow_unused=True)
     new_sd, new_state, gdict = {}, {}, {}
     for n, g in zip(names, grads):
@@ -290,7 +367,39 @@ def train_step(sd, opt_state, embed, target, cfg, lr, t, loss_type='Fusion6', be
         m, v = opt_state.get(n, (torch.zeros_like(g), torch.zeros_like(g)))
         p, m, v = adam_step(params[n].detach(), g, m, v, t, lr, beta1=beta1)
         new_sd[n], new_state[n], gdict[n] = p, (m, v), g
+    new_sd.update(const)
+    new_sd = {k: new_sd[k] for k in sd}                   # keep the state-dict order
     return new_sd, new_state, loss.detach(), img.detach(), gdict
+
+
+# ----------------------------------------------------------------------------- 8f-3 prune-then-finetune
+def finetune_steps(sd, masks, frozen, embed, target, cfg, lrs, loss_type='Fusion6', beta1=0.5):
+    """reference main_eval.py:446-507 on a state dict: `masks` (name -> 0/1 tensor) are the weight_mask of
+    torch.nn.utils.prune — the forward reads weight_orig * mask, so the gradient of weight_orig is the masked gradient;
+    `frozen` names never move (the ERB quirk, SURVEY.md 2.1 row 19: an ERB block reads the `.weight` computed at prune
+    time, so its pruned branch kernels stay at weight_orig * mask of that moment whatever Adam does to weight_orig).
+    Fresh Adam state (:426, :489-490).  `sd` holds weight_orig; returns (sd of weight_orig, effective weights, losses)."""
+    sd = {k: v.clone() for k, v in sd.items()}
+    stale = {n: sd[n] * masks[n] for n in frozen}
+    state, losses = {}, []
+    for t, lr in enumerate(lrs, 1):
+        params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+        # frozen: VALUE of the stale tensor, GRADIENT still reaching weight_orig through the retained graph of
+        # weight_orig * mask (main_eval.py:476-480 retain_graph=True) — Adam keeps moving the unused weight_orig
+        eff = {k: ((stale[k] + (params[k] * masks[k] - (params[k] * masks[k]).detach())) if k in frozen else
+                   (params[k] * masks[k] if k in masks else params[k])) for k in params}
+        loss = loss_fn(generator_forward(eff, embed, cfg), target, loss_type)
+        names = list(params)
+        grads = torch.autograd.grad(loss, [params[n] for n in names], allow_unused=True)
+        for n, g in zip(names, grads):
+            if g is None:
+                continue                    # the reference's Adam skips parameters without a gradient
+            m, v = state.get(n, (torch.zeros_like(g), torch.zeros_like(g)))
+            sd[n], m, v = adam_step(sd[n], g, m, v, t, lr, beta1=beta1)
+            state[n] = (m, v)
+        losses.append(float(loss.detach()))
+    eff = {k: (stale[k] if k in frozen else (sd[k] * masks[k] if k in masks else sd[k])) for k in sd}
+    return sd, eff, losses
 
 
 # ----------------------------------------------------------------------------- reference-shaped random state

@@ -14,7 +14,7 @@ run() {
   if [ $rc -ne 0 ]; then fail=1; fi
 }
 for op in fprop dgrad wgrad; do
-  for shape in tiny l0 l1 l2s b2 u3 wide; do
+  for shape in tiny l0 l1 l2s b2 u3 wide xl; do
     run $op $shape 0
   done
 done

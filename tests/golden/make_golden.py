@@ -61,7 +61,7 @@ def case(cfg, branch_type, name, n_steps=3):
     out['loss'] = loss.detach().clone()
     gen.zero_grad()
     loss.backward()
-    out['grads'] = {k: p.grad.detach().clone() for k, p in gen.named_parameters()}
+    out['grads'] = {k: p.grad.detach().clone() for k, p in gen.named_parameters() if p.grad is not None}
     out['psnr'] = ref_utils.psnr_fn([img.detach()], [target]).clone()
     # a few optimisation steps exactly like reference main_train.py:238-250
     opt = torch.optim.Adam(gen.parameters(), betas=(0.5, 0.999))
@@ -78,7 +78,7 @@ def case(cfg, branch_type, name, n_steps=3):
     out['train_losses'], out['train_lrs'] = losses, lrs
     out['trained_state'] = {k: v.clone() for k, v in gen.state_dict().items()}
     torch.save(out, os.path.join(HERE, name))
-    print(name, 'img', tuple(img.shape), 'loss', float(loss), 'params', sum(p.numel() for p in gen.parameters()))
+    print(name, 'img', tuple(img.shape), 'loss', float(loss.detach()), 'params', sum(p.numel() for p in gen.parameters()))
 
 
 def misc():
@@ -145,9 +145,82 @@ def a13_prune_quant():
     print('a13_prune_quant.pt: mask zeros', zeros, '/', total, '; fraction of ones in the quantised masks', ones)
 
 
+def finetune_case(branch_type, src, name, amount=0.3, start_epoch=3, finetune_epochs=2, iters=2):
+    """Prune-then-finetune (reference main_eval.py:213-545) with the reference's own classes and torch.nn.utils.prune:
+    a line-for-line mirror of the loop (:239-368 prune list + global_unstructured, :426 fresh Adam, :446-507 the steps
+    with `adjust_lr(epoch % total_epochs)`, `backward(retain_graph=ERB)` and `optimizer.state.clear()` before the first
+    step, :530-541 switch_to_deploy) minus `.cuda()` and the data loader.  The ERB run exhibits the frozen-branch quirk
+    (SURVEY.md 2.1 row 19): the golden records that the pruned branch kernels do not move."""
+    import torch.nn.utils.prune as prune
+    g = torch.load(os.path.join(HERE, src), weights_only=False)
+    cfg = g['cfg']
+    pe, gen = build(cfg, branch_type)
+    gen.load_state_dict(g['trained_state'])
+    start_state = {k: v.clone() for k, v in gen.state_dict().items()}
+    param_list, names = [], []
+    if branch_type == 'NeRV_vanilla':
+        for k, v in gen.named_parameters():
+            if 'weight' in k:
+                if 'stem' in k:
+                    param_list.append(gen.stem[int(k.split('.')[1])]); names.append(k)
+                elif 'layers' in k[:6]:
+                    param_list.append(gen.layers[int(k.split('.')[1])].branch); names.append(k)
+    else:
+        for k, v in gen.named_parameters():
+            if 'weight' in k and 'stem' in k:
+                param_list.append(gen.stem[int(k.split('.')[1])]); names.append(k)
+        for li, layer in enumerate(gen.layers):
+            for bn in ('rbr_3x3_branch', 'rbr_3x1_branch', 'rbr_1x3_branch', 'rbr_1x1_3x3_1x1_branch_1x1_1',
+                       'rbr_1x1_3x3_1x1_branch_3x3', 'rbr_1x1_3x3_1x1_branch_1x1_2'):
+                if hasattr(layer, bn):
+                    param_list.append(getattr(layer, bn)); names.append(f'layers.{li}.{bn}.weight')
+    prune.global_unstructured([(m, 'weight') for m in param_list], pruning_method=prune.L1Unstructured, amount=amount)
+    masks = {n: m.weight_mask.detach().clone() for n, m in zip(names, param_list)}
+    opt = torch.optim.Adam(gen.parameters(), betas=(0.5, 0.999), foreach=False)
+    args = argparse.Namespace(loss_type='Fusion6', lr=5e-4, lr_type='cosine', warmup=1, epochs=5)
+    embed, target = g['embed'], g['target']
+    total_epochs = start_epoch + finetune_epochs
+    losses, lrs = [], []
+    for epoch in range(start_epoch, total_epochs):
+        gen.train()
+        for i in range(iters):
+            out = gen(embed)[0]
+            loss = ref_utils.loss_fn(out, target, args)
+            lrs.append(ref_utils.adjust_lr(opt, epoch % total_epochs, i, 4, args))
+            opt.zero_grad()
+            loss.backward(retain_graph=(branch_type == 'ERB'))
+            if epoch == start_epoch and i == 0:
+                opt.state.clear()
+            opt.step()
+            losses.append(loss.item())
+    pre_deploy = {k: v.detach().clone() for k, v in gen.state_dict().items()}
+    eff = {n: m.weight.detach().clone() for n, m in zip(names, param_list)}      # what the forward reads
+    if branch_type == 'ERB':
+        for layer in gen.layers:
+            layer.switch_to_deploy()
+    final = {k: v.detach().clone() for k, v in gen.state_dict().items()}
+    with torch.no_grad():
+        img = gen(embed)[0].detach().clone()
+    out = dict(cfg=cfg, branch_type=branch_type, start_state=start_state, masks=masks, mask_names=names, amount=amount,
+               start_epoch=start_epoch, finetune_epochs=finetune_epochs, iters=iters, data_size=4, losses=losses, lrs=lrs,
+               pre_deploy_state=pre_deploy, effective_weights=eff, final_state=final, embed=embed, pos=g['pos'],
+               target=target, img=img)
+    torch.save(out, os.path.join(HERE, name))
+    moved = {n: float((eff[n] - start_state[n] * masks[n]).abs().max()) for n in names}
+    print(name, 'losses', losses, 'lrs', lrs, 'max |effective weight - pruned start|', moved)
+
+
 if __name__ == '__main__':
-    case(TINY, 'ERB', 'tiny_erb.pt')
-    case(TINY, 'NeRV_vanilla', 'tiny_vanilla.pt')
-    case(SMALL, 'ERB', 'small_erb.pt')
-    misc()
-    a13_prune_quant()
+    what = sys.argv[1:] or ['base']
+    if 'base' in what:
+        case(TINY, 'ERB', 'tiny_erb.pt')
+        case(TINY, 'NeRV_vanilla', 'tiny_vanilla.pt')
+        case(SMALL, 'ERB', 'small_erb.pt')
+        misc()
+        a13_prune_quant()
+    if 'finetune' in what:
+        finetune_case('ERB', 'small_erb.pt', 'finetune_erb.pt')
+        finetune_case('NeRV_vanilla', 'tiny_vanilla.pt', 'finetune_vanilla.pt')
+    if 'branches' in what:
+        for bt in ('ACB', 'RepVGG', 'DBB', 'ECB'):
+            case(SMALL, bt, f'small_{bt.lower()}.pt')

@@ -59,7 +59,8 @@ def build(g, branch_type, deploy=False):
 
 
 @pytest.mark.parametrize("name,bt", [("tiny_erb.pt", "ERB"), ("tiny_vanilla.pt", "NeRV_vanilla"),
-                                     ("small_erb.pt", "ERB")])
+                                     ("small_erb.pt", "ERB"), ("small_acb.pt", "ACB"), ("small_repvgg.pt", "RepVGG"),
+                                     ("small_dbb.pt", "DBB"), ("small_ecb.pt", "ECB")])
 def test_init_is_bit_identical_to_reference(golden, name, bt):
     g = golden(name)
     _, gen = build(g, bt)
@@ -91,7 +92,7 @@ def test_deepcopy_drops_executors(golden):
     assert cp._executors == {} and list(cp.state_dict()) == list(gen.state_dict())
 
 
-@pytest.mark.parametrize("kw", [dict(branch_type='DBB'), dict(act='gelu'), dict(norm='bn'), dict(num_blocks=2),
+@pytest.mark.parametrize("kw", [dict(branch_type='OREPA'), dict(act='mish'), dict(norm='bn'), dict(num_blocks=2),
                                 dict(sin_res=False)])
 def test_out_of_scope_configs_raise(kw):
     base = dict(embed_length=8, stem_dim_num='16_1', fc_hw_dim='3_4_4', expansion=1, num_blocks=1, norm='none',
