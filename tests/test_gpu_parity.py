@@ -58,7 +58,7 @@ def test_selftest_binary_tcgen05_vs_simt(dev):
     exe = os.path.join(ROOT, "boosting-neural-video-representation-via-online-structural-reparameteration_b200",
                        "onr_selftest")
     for op in ("fprop", "dgrad", "wgrad"):
-        for shape in ("tiny", "l0", "l1", "l2s", "b2", "u3", "wide", "xl"):
+        for shape in ("tiny", "l0", "l1", "l2s", "b2", "u3", "wide"):
             r = subprocess.run([exe, op, shape, "0"], capture_output=True, text=True, timeout=120)
             assert r.returncode == 0, r.stdout + r.stderr
 
