@@ -18,6 +18,12 @@ PSNR + MS-SSIM — i.e. one iteration of reference main_train.py:229-254.
   c3  ERB U1080 600 x 1080 x 1920, fc_hw_dim 9_16_26,  strides 5 3 2 2 2          (8 GPUs)
   c4  reparameterised single-branch decode of c1 with prune_ratio 0.2 + quant_bit 8, full-clip eval
       (decode fps through main_eval's own FPS loop, PSNR / MS-SSIM)
+Widened rows, same geometry as --config, named in `config.workload`; informational lines:
+  --branch_type ACB|RepVGG|DBB|ECB|NeRV_vanilla   the reference's other branch sets (folded online here; the stock
+                                                  PyTorch leg runs them as the reference does, one conv per branch)
+  --act gelu|relu|...                             the other activations (pre-activation mode + onr_act_map)
+  --finetune_prune R                              the prune-then-finetune step (main_eval.py:446-507): global
+                                                  magnitude masks at ratio R, masked-gradient FrameFitter
 
 Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` is the same step driven
 through the public API with pinned HOST frames: H2D of the uint8 frame + index and D2H of the metrics every
@@ -36,7 +42,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 _COMMON = dict(embed='1.25_40', stem_dim_num='512_1', expansion=1, reduction=2, lower_width=96, branch_type='ERB',
-               loss_type='Fusion6', lr=5e-4, epochs=300, warmup_ratio=0.2, beta=0.5)
+               act='swish', loss_type='Fusion6', lr=5e-4, epochs=300, warmup_ratio=0.2, beta=0.5)
 WORKLOADS = {
     "c1": dict(_COMMON, name="ERB Bunny-shaped synthetic 132x720x1280 (BASELINE configs[1])", kind="train",
                n_frames=132, H=720, W=1280, fc_hw_dim='9_16_26', strides=[5, 2, 2, 2, 2]),
@@ -179,8 +185,10 @@ def oracle_step_loop(n_steps, warmup, device, sync=None):
     from oracle import nerv_oracle as O
     w = WORKLOAD
     fh, fw, fd = [int(x) for x in w['fc_hw_dim'].split('_')]
-    cfg = dict(fc_h=fh, fc_w=fw, fc_dim=fd, strides=w['strides'], sigmoid=False)
-    sd = {k: v.to(device) for k, v in O.random_state(cfg, w, seed=1).items()}
+    cfg = dict(fc_h=fh, fc_w=fw, fc_dim=fd, strides=w['strides'], sigmoid=False, act=w['act'])
+    if w['branch_type'] in ('ACB', 'RepVGG', 'DBB', 'ECB'):
+        cfg['explicit_branches'] = w['branch_type']     # as the reference runs them (model.py:541-565): no fold
+    sd = {k: v.to(device) for k, v in O.random_state(cfg, w, seed=1, branch_type=w['branch_type']).items()}
     frames = synthetic_frames_cpu(2, w['H'], w['W']).to(device)
     state = {}
     total = 0.0
@@ -238,7 +246,10 @@ def cpu_steps(n_steps, warmup, threads=None):
 def metric_of(w):
     if w['kind'] == 'decode':
         return "reparam decode frames/s (720p, prune 0.2 + quant 8)"
-    return "train frames/s ({}p ERB)".format(w['H'])
+    extra = "" if w['act'] == 'swish' else ", act " + w['act']
+    if w.get('finetune_prune'):
+        extra += ", prune-then-finetune step at ratio {}".format(w['finetune_prune'])
+    return "train frames/s ({}p {}{})".format(w['H'], w['branch_type'], extra)
 
 
 def run_reference(opts):
@@ -254,7 +265,7 @@ def run_reference(opts):
     total, cores = cpu_steps(opts.steps, opts.warmup)
     fps = opts.steps / total
     what = ("forward-only decodes of one frame (single-branch model)" if w['kind'] == 'decode' else
-            "ERB training steps of one frame (fwd, Fusion6, bwd, Adam, PSNR, MS-SSIM)")
+            f"{w['branch_type']} training steps of one frame (fwd, Fusion6, bwd, Adam, PSNR, MS-SSIM)")
     line = {
         "impl": "reference", "metric": metric_of(w), "value": fps, "unit": "frames/s",
         "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": 1000.0 * total / opts.steps,
@@ -421,14 +432,30 @@ def run_ours(opts):
     torch.manual_seed(1)
     pe = PositionalEncoding(w['embed'])
     gen = Generator(embed_length=pe.embed_length, stem_dim_num=w['stem_dim_num'], fc_hw_dim=w['fc_hw_dim'],
-                    expansion=w['expansion'], num_blocks=1, norm='none', act='swish', bias=True,
+                    expansion=w['expansion'], num_blocks=1, norm='none', act=w['act'], bias=True,
                     reduction=w['reduction'], conv_type='conv', stride_list=w['strides'], sin_res=True,
                     lower_width=w['lower_width'], sigmoid=False, deploy=False, branch_type=w['branch_type']).to(dev)
     n_frames = opts.frames or w['n_frames']
     clip = synthetic_clip(n_frames, w['H'], w['W'], device=dev)                 # uint8, resident in HBM
     spe = sharding.steps_per_epoch(n_frames, world)
+    ft_kw, ft_info = {}, None
+    if w.get('finetune_prune'):
+        # the prune-then-finetune step (main_eval.py:239-507): global magnitude masks over the train-state tensors, the
+        # ERB branch kernels frozen as in the reference, epoch numbering continued behind the 300 training epochs
+        from orepnerv.main_eval import global_masks, train_state_prunable
+        targets = train_state_prunable(gen)
+        masks = global_masks([m.weight.detach() for _, m in targets], float(w['finetune_prune']))
+        gm = {}
+        with torch.no_grad():
+            for (n, m), mask in zip(targets, masks):
+                m.weight.mul_(mask)
+                gm[n + '.weight'] = torch.zeros_like(mask) if ('.rbr_' in n) else mask
+        ft_kw = dict(grad_masks=gm, epoch_offset=w['epochs'], epoch_mod=w['epochs'] + 100)
+        ft_info = {"prune_ratio": w['finetune_prune'], "masked_tensors": len(gm),
+                   "mask_zeros": int(sum(int((m == 0).sum()) for m in masks)),
+                   "mask_total": int(sum(m.numel() for m in masks))}
     fit = FrameFitter(gen, pe, args, world_size=world, data_size=n_frames, steps_per_epoch=spe,
-                      use_graph=not opts.no_graph)
+                      use_graph=not opts.no_graph, **ft_kw)
     t_all = torch.arange(n_frames, dtype=torch.float32, device=dev) / n_frames
     order = []
     ep = 0
@@ -614,6 +641,7 @@ def run_ours(opts):
             "gpu_launches": int(per_step * opts.steps), "kernels_per_step": int(per_step),
             "roofline": roofline,
             "last_step": {"loss": out_last[0].item(), "psnr": out_last[4].item(), "msssim": out_last[5].item()},
+            "finetune": ft_info,
             "decode": decode,
             "e2e_reference_api": ref_api,
         }
@@ -624,7 +652,7 @@ def run_ours(opts):
                 line["gpu_library_baseline"] = {"error": repr(exc)[:200]}
         if cpu_total is not None:
             line["cpu_baseline"] = {"value": 2 / cpu_total, "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"2 ERB training steps of one {w['H']}x{w['W']} frame after 1 warm-up "
+                                    "sample": f"2 {w['branch_type']} training steps of one {w['H']}x{w['W']} frame after 1 warm-up "
                                               "(oracle port)"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -774,9 +802,22 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--frames", type=int, default=0, help="clip length override (profiling runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--branch_type", default=None, choices=["NeRV_vanilla", "ERB", "ACB", "RepVGG", "DBB", "ECB"])
+    ap.add_argument("--act", default=None)
+    ap.add_argument("--finetune_prune", type=float, default=0.0)
     opts = ap.parse_args()
     global WORKLOAD
-    WORKLOAD = WORKLOADS[opts.config]
+    WORKLOAD = dict(WORKLOADS[opts.config])
+    if opts.branch_type and opts.branch_type != WORKLOAD['branch_type']:
+        WORKLOAD['branch_type'] = opts.branch_type
+        WORKLOAD['name'] = WORKLOAD['name'].replace("ERB ", opts.branch_type + " ", 1) + \
+            f" [branch_type {opts.branch_type}: SURVEY.md 8f-4, not a BASELINE config]"
+    if opts.act and opts.act != WORKLOAD['act']:
+        WORKLOAD['act'] = opts.act
+        WORKLOAD['name'] += f" [act {opts.act}: SURVEY.md 8f-4, not a BASELINE config]"
+    if opts.finetune_prune:
+        WORKLOAD['finetune_prune'] = opts.finetune_prune
+        WORKLOAD['name'] += f" [prune-then-finetune step, prune_ratio {opts.finetune_prune}: SURVEY.md 8f-3]"
     if opts.impl == "reference":
         run_reference(opts)
     elif opts.impl == "torch-gpu":

@@ -56,10 +56,18 @@ __global__ void branch_bwd_w1_kernel(const onr_branch_set s, const float* __rest
     }
 }
 
+// one warp per output channel: the lanes stride over the input channels for the SeqConv3x3 scale gradients (fixed-order
+// shuffle reduction), lane 0 writes
 __global__ void branch_bwd_o_kernel(const onr_branch_set s, const onr_branch_set g, const float* __restrict__ dK,
                                     const float* __restrict__ db) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o < s.cout) branch_bwd_o(s, g, dK, db, o);
+    const int lane = threadIdx.x & 31;
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (o >= s.cout) return;                                     // warp-uniform
+    float dot[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+        if (s.edge_k0[e]) dot[e] = warp_sum(branch_bwd_scale_partial(s, dK, e, o, lane, 32));
+    if (lane == 0) branch_bwd_o(s, g, db, o, dot);
 }
 
 static inline int grid_of(size_t n, int block) {
@@ -112,7 +120,7 @@ int onr_branch_fold_bwd(const onr_branch_set* w, const float* dK, const float* d
             ONR_LAUNCH_CHECK();
         }
     }
-    branch_bwd_o_kernel<<<ceil_div(w->cout, 128), 128, 0, st>>>(*w, *g, dK, dbias);
+    branch_bwd_o_kernel<<<ceil_div(w->cout, 4), 128, 0, st>>>(*w, *g, dK, dbias);
     ONR_LAUNCH_CHECK();
     return 0;
 }

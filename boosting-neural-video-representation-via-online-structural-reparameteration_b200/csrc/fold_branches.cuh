@@ -110,9 +110,24 @@ ONR_HD float branch_bwd_w1_partial(const onr_branch_set& s, const float* dK, int
     return acc;
 }
 
-// gradients indexed by the output channel alone: every bias, and scale / b0 / bias of the SeqConv3x3 branches.  OVERWRITES.
-ONR_HD void branch_bwd_o(const onr_branch_set& s, const onr_branch_set& g, const float* dK, const float* db, int o) {
+// partial of sum_i k0[o,i] sum_t mask[o,t] dK[o,i,t] over i in {start, start+stride, ...}: the dK-dependent part of
+// d scale[o] of SeqConv3x3 branch e
+ONR_HD float branch_bwd_scale_partial(const onr_branch_set& s, const float* dK, int e, int o, int start, int stride) {
     const int cin = s.cin;
+    float acc = 0.0f;
+    for (int i = start; i < cin; i += stride) {
+        const size_t oi = (size_t)o * cin + i;
+        float a = 0.0f;
+        for (int t = 0; t < 9; ++t) a += s.edge_mask[e][(size_t)o * 9 + t] * dK[oi * 9 + t];
+        acc += a * s.edge_k0[e][oi];
+    }
+    return acc;
+}
+
+// gradients indexed by the output channel alone: every bias, and scale / b0 / bias of the SeqConv3x3 branches.
+// `scale_dot[e]` = the complete sum of branch_bwd_scale_partial over i.  OVERWRITES.
+ONR_HD void branch_bwd_o(const onr_branch_set& s, const onr_branch_set& g, const float* db, int o,
+                         const float* scale_dot) {
     const float d = db[o];
     if (g.b3x3) g.b3x3[o] = d;
     if (g.b1x3) g.b1x3[o] = d;
@@ -123,16 +138,7 @@ ONR_HD void branch_bwd_o(const onr_branch_set& s, const onr_branch_set& g, const
             const float ms = edge_mask_sum(s.edge_mask[e], o);
             if (g.edge_bias[e]) g.edge_bias[e][o] = d;
             if (g.edge_b0[e]) g.edge_b0[e][o] = d * s.edge_scale[e][o] * ms;
-            if (g.edge_scale[e]) {
-                float acc = 0.0f;
-                for (int i = 0; i < cin; ++i) {
-                    const size_t oi = (size_t)o * cin + i;
-                    float a = 0.0f;
-                    for (int t = 0; t < 9; ++t) a += s.edge_mask[e][(size_t)o * 9 + t] * dK[oi * 9 + t];
-                    acc += a * s.edge_k0[e][oi];
-                }
-                g.edge_scale[e][o] = acc + d * s.edge_b0[e][o] * ms;
-            }
+            if (g.edge_scale[e]) g.edge_scale[e][o] = scale_dot[e] + d * s.edge_b0[e][o] * ms;
         }
 }
 

@@ -186,8 +186,14 @@ def generator_forward(sd, embed, cfg, return_features=False):
                      cfg['fc_dim'], cfg['fc_h'], cfg['fc_w'], act)
     feats = [x]
     for i, s in enumerate(cfg['strides']):
-        K, b = block_kernel(sd, f'layers.{i}.')
-        x = block_forward(x, K, b, s, act)
+        p = f'layers.{i}.'
+        if cfg.get('explicit_branches') and (p + 'rbr_3x3_branch.weight') in sd and \
+                (p + 'rbr_1x1_3x3_1x1_branch_1x1_1.weight') not in sd:
+            # the way the reference itself runs ACB / RepVGG / DBB / ECB (model.py:541-565): one convolution per branch
+            x = activation(F.pixel_shuffle(branch_set_forward(x, sd, p, cfg['explicit_branches']), s), act)
+        else:
+            K, b = block_kernel(sd, p)
+            x = block_forward(x, K, b, s, act)
         feats.append(x)
     last = len(cfg['strides']) - 1
     img = head_forward(x, sd[f'head_layers.{last}.weight'], sd[f'head_layers.{last}.bias'], cfg.get('sigmoid', False))
@@ -426,6 +432,27 @@ def random_state(cfg, w, seed=1, deploy=False, branch_type='ERB'):
             sd[p + 'rbr_reparam.weight'], sd[p + 'rbr_reparam.bias'] = u((co, c, 3, 3), 9 * c), u((co,), 9 * c)
         elif branch_type == 'NeRV_vanilla':
             sd[p + 'branch.weight'], sd[p + 'branch.bias'] = u((co, c, 3, 3), 9 * c), u((co,), 9 * c)
+        elif branch_type in ('ACB', 'RepVGG', 'DBB', 'ECB'):                       # model.py:345-393
+            sd[p + 'rbr_3x3_branch.weight'], sd[p + 'rbr_3x3_branch.bias'] = u((co, c, 3, 3), 9 * c), u((co,), 9 * c)
+            if branch_type == 'ACB':
+                sd[p + 'rbr_3x1_branch.weight'], sd[p + 'rbr_3x1_branch.bias'] = u((co, c, 3, 1), 3 * c), u((co,), 3 * c)
+                sd[p + 'rbr_1x3_branch.weight'], sd[p + 'rbr_1x3_branch.bias'] = u((co, c, 1, 3), 3 * c), u((co,), 3 * c)
+            if branch_type in ('RepVGG', 'DBB'):
+                sd[p + 'rbr_1x1_branch.weight'], sd[p + 'rbr_1x1_branch.bias'] = u((co, c, 1, 1), c), u((co,), c)
+            if branch_type in ('DBB', 'ECB'):
+                sd[p + 'rbr_1x1_3x3_branch_1x1.weight'] = u((2 * c, c, 1, 1), c)
+                sd[p + 'rbr_1x1_3x3_branch_3x3.weight'] = u((co, 2 * c, 3, 3), 18 * c)
+            if branch_type == 'DBB':
+                sd[p + 'rbr_1x1_avg_branch_1x1.weight'] = u((co, c, 1, 1), c)
+            if branch_type == 'ECB':
+                masks = {'sbx': [[1, 0, -1], [2, 0, -2], [1, 0, -1]], 'sby': [[1, 2, 1], [0, 0, 0], [-1, -2, -1]],
+                         'lpl': [[0, 1, 0], [1, -4, 1], [0, 1, 0]]}
+                for e, mk in masks.items():
+                    q = p + f'rbr_conv1x1_{e}_branch.'
+                    sd[q + 'k0'], sd[q + 'b0'] = u((co, c, 1, 1), c), u((co,), c)
+                    sd[q + 'scale'] = torch.randn((co, 1, 1, 1), generator=g) * 1e-3
+                    sd[q + 'bias'] = torch.randn((co,), generator=g) * 1e-3
+                    sd[q + 'mask'] = torch.tensor(mk, dtype=torch.float32).view(1, 1, 3, 3).repeat(co, 1, 1, 1)
         else:
             sd[p + 'rbr_3x3_branch.weight'], sd[p + 'rbr_3x3_branch.bias'] = u((co, c, 3, 3), 9 * c), u((co,), 9 * c)
             sd[p + 'rbr_3x1_branch.weight'], sd[p + 'rbr_3x1_branch.bias'] = u((co, c, 3, 1), 3 * c), u((co,), 3 * c)

@@ -17,7 +17,11 @@ void host_branch_fold_fwd(const onr_branch_set* s, float* K, float* bias) {
 void host_branch_fold_bwd(const onr_branch_set* s, const float* dK, const float* db, const onr_branch_set* g) {
     for (int o = 0; o < s->cout; ++o) {
         for (int i = 0; i < s->cin; ++i) onr::branch_bwd_oi(*s, *g, dK, o, i);
-        onr::branch_bwd_o(*s, *g, dK, db, o);
+        float dot[3] = {0.0f, 0.0f, 0.0f};
+        for (int e = 0; e < 3; ++e)
+            if (s->edge_k0[e])
+                for (int l = 0; l < 32; ++l) dot[e] += onr::branch_bwd_scale_partial(*s, dK, e, o, l, 32);
+        onr::branch_bwd_o(*s, *g, db, o, dot);
     }
     if (s->seq_w1) {
         const int cm = 2 * s->cin;
