@@ -29,15 +29,19 @@ __global__ void pe_layer1_kernel(const float* __restrict__ t_norm, const float* 
             const float s = sinf(v), c = cosf(v);
             se[2 * i] = s;
             se[2 * i + 1] = c;
-            embed[(size_t)b * E + 2 * i] = s;
-            embed[(size_t)b * E + 2 * i + 1] = c;
+            if (blockIdx.y == 0) {
+                embed[(size_t)b * E + 2 * i] = s;
+                embed[(size_t)b * E + 2 * i + 1] = c;
+            }
         }
     } else {
         // the caller already holds the embedding (Generator.forward(embed) of the reference API)
         for (int i = threadIdx.x; i < E; i += blockDim.x) se[i] = embed[(size_t)b * E + i];
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+    // the hidden units are spread over gridDim.y blocks (every block recomputes the 2*levels encoding values, which is
+    // cheaper than one SM pulling all of W1 through its own load path); the per-unit arithmetic order is unchanged
+    for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < hid; j += gridDim.y * blockDim.x) {
         const float* w = W1 + (size_t)j * E;
         float acc = 0.0f;
         for (int e = 0; e < E; ++e) acc = fmaf(w[e], se[e], acc);
@@ -392,8 +396,8 @@ int onr_pe_stem_fwd_act(const float* t_norm, int B, const float* freqs, int leve
     ONR_REQUIRE(act >= 0 && act < kActCount, "stem: unknown activation code %d", act);
     ONR_REQUIRE(B >= 1 && levels >= 1 && hid % 4 == 0 && Cp % 32 == 0 && Cp >= fc_dim, "stem: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
-    pe_layer1_kernel<<<B, 256, 2 * levels * sizeof(float), st>>>(t_norm, freqs, levels, W1, b1, hid, embed,
-                                                                 pre1, h1, act);
+    pe_layer1_kernel<<<dim3(B, ceil_div(hid, 64)), 64, 2 * levels * sizeof(float), st>>>(t_norm, freqs, levels, W1, b1,
+                                                                                         hid, embed, pre1, h1, act);
     ONR_LAUNCH_CHECK();
     const int total = fh * fw * Cp;
     const int wpb = 8;

@@ -372,7 +372,8 @@ class NetExecutor:
         if t_norm is None:
             if embed is None:
                 raise ValueError("forward needs embed or t_norm")
-            self.embed.copy_(embed.reshape(self.B, self.E))
+            if embed.data_ptr() != self.embed.data_ptr():
+                self.embed.copy_(embed.reshape(self.B, self.E))
         elif freqs is None:
             raise ValueError("t_norm needs the frequency table of the PositionalEncoding")
         check(self.lib.onr_pe_stem_fwd_act(
@@ -401,6 +402,33 @@ class NetExecutor:
             ptr(self.x[self.L]), self.B, self.H, self.W, self.C_last, self.geoms[-1].cpo,
             ptr(head.weight), ptr(head.bias), 1 if gen.sigmoid else 0, ptr(self.img), st), "onr_head_fwd")
         return self.img
+
+    # ------------------------------------------------------------------------------------- decode
+    def decode(self, embed):
+        """Decode (reference main_eval.py:753-762 `model(embed_input)` under no_grad) as ONE CUDA-graph replay: stem,
+        the block convolutions and the head are captured once per set of packed weights — a 720p decode is eight
+        kernels of 5-160 us, so the launch gaps of eager issue are a visible share of the frame.  Weights are re-folded /
+        re-packed eagerly (outside the graph) whenever a parameter changed, which also drops the captured graph.
+        Returns a fresh image tensor, like the reference.  ONR_DECODE_GRAPH=0 keeps the eager launches."""
+        assert not self.train
+        if os.environ.get("ONR_DECODE_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
+            img = torch.empty(self.B, 3, self.H, self.W, dtype=torch.float32, device=self.dev)
+            self.forward(embed=embed, out=img)
+            return img
+        stale = self._weights_key() != getattr(self, "_packed_key", None)
+        if stale or getattr(self, "_decode_graph", None) is None:
+            self._decode_graph = None
+            self.forward(embed=embed)                     # eager: refreshes the operands; the warm-up of the capture
+            out = self._img_static.clone()
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.forward(embed=self.embed, refresh=False)
+            self._decode_graph = g
+            return out
+        self.embed.copy_(embed.reshape(self.B, self.E))
+        self._decode_graph.replay()
+        return self._img_static.clone()
 
     # ------------------------------------------------------------------------------------ backward
     def backward(self, gimg, grads, block_hook=None, reduce=None):

@@ -474,6 +474,5 @@ class Generator(nn.Module):
             img = _GeneratorFunction.apply(self, ex, input.detach(), *params)
         else:
             with torch.no_grad():
-                img = torch.empty(B, 3, ex.H, ex.W, dtype=torch.float32, device=ex.dev)
-                ex.forward(embed=input, out=img)
+                img = ex.decode(input)
         return [img]

@@ -340,3 +340,34 @@ def test_prune_finetune_workflow(dev, golden, bt, tmp_path):
     prune_and_quantise(gen, args, 4, (H, W), prune_now=False)
     res = decode_clip(gen, pe, Clip(), args, fwd_num=1, quiet=True)
     assert res['frames'] == 4 and res['psnr'] > 3 and torch.isfinite(torch.tensor(res['psnr']))
+
+
+# ------------------------------------------------------------------------------------------- decode as one CUDA graph
+def test_decode_graph_matches_eager(dev, golden, monkeypatch):
+    """Generator.__call__ under no_grad replays one captured graph per set of packed weights: identical images to the
+    eager launches, a fresh tensor per call, and a parameter change (in place or through FrameFitter's raw pointers)
+    re-packs and re-captures."""
+    g = golden("small_erb.pt")
+    pe, dep = build(g['cfg'], "ERB", dev, deploy=True)
+    dep.load_state_dict(g['deploy_state'])
+    dep.eval()
+    ts = torch.tensor([[0.1], [0.5], [0.9]], device=dev)
+    with torch.no_grad():
+        embeds = [pe(t) for t in ts]
+        graph_imgs = [dep(e)[0] for e in embeds] + [dep(embeds[0])[0]]
+        assert graph_imgs[0].data_ptr() != graph_imgs[3].data_ptr() and torch.equal(graph_imgs[0], graph_imgs[3])
+        assert not torch.equal(graph_imgs[0], graph_imgs[1])
+        monkeypatch.setenv("ONR_DECODE_GRAPH", "0")
+        eager = [dep(e)[0] for e in embeds]
+        monkeypatch.delenv("ONR_DECODE_GRAPH")
+        for a, b in zip(graph_imgs, eager):
+            assert torch.equal(a, b)
+        assert rel_l2(graph_imgs[0], O.generator_forward(g['deploy_state'], embeds[0].cpu(), ocfg(g['cfg']))) <= 1e-2
+        dep.layers[0].rbr_reparam.weight.mul_(1.5)               # in-place change: version bump -> re-pack, re-capture
+        dep.head_layers[1].bias.add_(0.25)                       # head parameters are read by pointer at replay
+        changed = dep(embeds[0])[0]
+        assert not torch.equal(changed, graph_imgs[0])
+        monkeypatch.setenv("ONR_DECODE_GRAPH", "0")
+        assert torch.equal(changed, dep(embeds[0])[0])
+        monkeypatch.delenv("ONR_DECODE_GRAPH")
+        assert torch.equal(changed, dep(embeds[0])[0])           # replay of the re-captured graph
