@@ -163,43 +163,44 @@ def build_model(args, device, deploy=None):
 class FrameCache:
     """The whole clip as uint8 [N,3,H,W] resident in HBM plus the normalised indices i/N — the on-GPU
     replacement of reference CustomDataSet (model.py:11-70): same sorted file listing, `vid_list` / `frame_gap`
-    sub-sampling, portrait frames transposed, index i/N.  365 MB for Bunny, 3.7 GB for a 600-frame 1080p clip."""
+    sub-sampling, portrait frames transposed, index i/N.  365 MB for Bunny, 3.7 GB for a 600-frame 1080p clip.
+
+    Sample k of the reference is (image of listing position k*frame_gap, frame_idx[k*frame_gap]) with
+    `frame_idx = [i/N_listing]`, filtered to `vid_list` when one is given, and `len = len(frame_idx) // frame_gap`
+    (model.py:37-44, :57-70).  Note what that means for `--vid`: the INDICES are those of the selected frames but the
+    IMAGES are still taken from the head of the listing (`frame_path` is never filtered, model.py:58-59) — kept as is,
+    the cache reproduces the reference's samples, not its intent."""
 
     def __init__(self, dataset, device, vid_list=(None,), frame_gap=1):
         m = re.fullmatch(r'synthetic:(\d+)x(\d+)x(\d+)', dataset)
         if m:
-            n, h, w = (int(x) for x in m.groups())
-            frames = synthetic_clip(n, h, w, device=device)
+            n_listing, h, w = (int(x) for x in m.groups())
+            load = None
         else:
-            frames = self._load_dir(f'../data/{dataset.lower()}', vid_list).to(device)
-        # reference model.py:26-44: the normalised index is i / N over the WHOLE sorted listing, computed before the
-        # --vid selection (frames come back with their listing positions), and __len__ is N // frame_gap
-        positions, n_listing = getattr(self, '_positions', None), getattr(self, '_n_listing', None)
-        n_all = frames.size(0)
-        if positions is None:
-            positions, n_listing = list(range(n_all)), n_all
-        idx_all = [float(pos) / n_listing for pos in positions]            # reference model.py:37
-        keep = [i * frame_gap for i in range(n_all // frame_gap)]          # reference model.py:40-44, :57
-        self.frames = frames[keep].contiguous()
-        self.t = torch.tensor([idx_all[i] for i in keep], dtype=torch.float32, device=device)
+            main_dir = f'../data/{dataset.lower()}'
+            names = sorted(os.listdir(main_dir))                            # reference model.py:27-28
+            n_listing = len(names)
+            load = lambda pos: self._load_image(os.path.join(main_dir, names[pos]))    # noqa: E731
+        frame_idx = [float(i) / n_listing for i in range(n_listing)]       # reference model.py:37
+        if vid_list is not None and None not in list(vid_list):
+            frame_idx = [frame_idx[i] for i in vid_list]                    # reference model.py:40-41
+        valid = [k * frame_gap for k in range(len(frame_idx) // frame_gap)]    # reference model.py:50, :57
+        if load is None:
+            frames = synthetic_clip(n_listing, h, w, device=device)[valid]
+        else:
+            frames = torch.stack([load(v) for v in valid]).to(device)
+        self.frames = frames.contiguous()
+        self.t = torch.tensor([frame_idx[v] for v in valid], dtype=torch.float32, device=device)
 
-    def _load_dir(self, main_dir, vid_list):
+    @staticmethod
+    def _load_image(path):
         import numpy as np
         from PIL import Image
-        names = sorted(os.listdir(main_dir))
-        positions = list(range(len(names)))
-        if vid_list and vid_list[0] is not None:
-            positions = [i for i in positions if i in set(vid_list)]
-        self._positions, self._n_listing = positions, len(names)
-        names = [names[i] for i in positions]
-        out = []
-        for n in names:
-            img = np.asarray(Image.open(os.path.join(main_dir, n)).convert('RGB'))
-            t = torch.from_numpy(img.copy()).permute(2, 0, 1)
-            if t.size(1) > t.size(2):                                       # reference model.py:66-67
-                t = t.permute(0, 2, 1)
-            out.append(t)
-        return torch.stack(out).contiguous()
+        img = np.asarray(Image.open(path).convert('RGB'))                   # reference model.py:60
+        t = torch.from_numpy(img.copy()).permute(2, 0, 1)                   # uint8 [3,H,W]; k/255 on the device == ToTensor
+        if t.size(1) > t.size(2):                                           # reference model.py:66-67
+            t = t.permute(0, 2, 1)
+        return t
 
     def __len__(self):
         return self.frames.size(0)

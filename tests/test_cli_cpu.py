@@ -80,3 +80,71 @@ def test_every_reference_flag_exists_with_the_same_default():
                 assert act.default is False and act.nargs == 0, (script, spec['flags'])
             if 'nargs' in spec:
                 assert act.nargs == spec['nargs'], (script, spec['flags'])
+
+
+def _write_clip(root, n=7, h=6, w=9, portrait_at=2):
+    import numpy as np
+    from PIL import Image
+    import os
+    d = os.path.join(root, "data", "clipx")
+    os.makedirs(d)
+    rng = np.random.RandomState(0)
+    for i in range(n):
+        shape = (w, h, 3) if i == portrait_at else (h, w, 3)            # one portrait frame (transposed on load)
+        Image.fromarray(rng.randint(0, 256, shape, dtype=np.uint8)).save(os.path.join(d, f"f{i:03d}.png"))
+    os.makedirs(os.path.join(root, "run"))
+    return os.path.join(root, "run")
+
+
+def test_frame_cache_reproduces_the_reference_dataset(tmp_path, monkeypatch):
+    """FrameCache (directory branch: PIL decode once, uint8, portrait transpose, i/N index, --vid / frame_gap) against
+    the UNMODIFIED reference CustomDataSet (model.py:11-70) on the same directory of PNG frames — including its
+    `--vid` behaviour (indices of the selection, images from the head of the listing)."""
+    import os
+    import sys
+    import numpy as np
+    import pytest
+    from orepnerv.cli_common import FrameCache
+    run = _write_clip(str(tmp_path))
+    monkeypatch.chdir(run)                                                  # the reference reads ../data/<dataset>
+    cases = [dict(vid_list=[None], frame_gap=1), dict(vid_list=[None], frame_gap=3), dict(vid_list=[1, 4, 6, 2], frame_gap=1),
+             dict(vid_list=[5, 0, 3], frame_gap=2)]
+    caches = [FrameCache("ClipX", torch.device("cpu"), **kw) for kw in cases]
+    c0 = caches[0]
+    assert c0.frames.dtype == torch.uint8 and tuple(c0.frames.shape) == (7, 3, 6, 9)
+    assert torch.equal(c0.t, torch.arange(7, dtype=torch.float32) / 7)
+    assert len(caches[1]) == 2 and len(caches[2]) == 4 and len(caches[3]) == 1
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("the reference tree is not on this machine: checked the layout only")
+    sys.path.insert(0, "/root/reference")
+    monkeypatch.setattr(np, "asfarray", lambda a: np.asarray(a, dtype=float), raising=False)   # removed in NumPy 2
+    import model as ref_model                                               # reference, unmodified
+    from torchvision import transforms
+    for kw, cache in zip(cases, caches):
+        ds = ref_model.CustomDataSet("../data/clipx", transforms.ToTensor(), **kw)
+        assert len(ds) == len(cache), kw
+        for k in range(len(ds)):
+            img, idx = ds[k]
+            assert torch.equal(cache.frames[k].float().div(255), img), (kw, k)     # bit-identical to ToTensor
+            assert cache.t[k].item() == idx.item(), (kw, k)
+
+
+def test_cli_accepts_the_widened_rows_and_rejects_the_rest():
+    import pytest
+    base = [a for a in README_FLAGS]
+    for extra in (['--branch_type', 'DBB'], ['--branch_type', 'ECB', '--act', 'gelu'], ['--act', 'leaky01'],
+                  ['--fc_hw_dim', '9_16_128', '--expansion', '8']):
+        args = finish_args(build_parser().parse_args(base + extra))
+        assert args.branch_type in ('ERB', 'DBB', 'ECB')
+    ev = finish_args(build_parser(eval_mode=True).parse_args(base + ['--prune_ratio', '0.4', '--finetune',
+                                                                     '--finetune_epochs', '5']))
+    assert ev.finetune and ev.finetune_epochs == 5
+    for extra in (['--norm', 'bn'], ['--num_blocks', '2'], ['--conv_type', 'deconv'], ['--loss_type', 'Fusion10']):
+        with pytest.raises(SystemExit):
+            finish_args(build_parser().parse_args(base + extra))
+    no_single = [a for a in base if a != '--single_res']
+    with pytest.raises(SystemExit):
+        finish_args(build_parser().parse_args(no_single))
+    with pytest.raises(SystemExit):                                         # the reference finetunes NeRV_vanilla | ERB only
+        finish_args(build_parser(eval_mode=True).parse_args(base + ['--branch_type', 'DBB', '--prune_ratio', '0.4',
+                                                                    '--finetune']))
