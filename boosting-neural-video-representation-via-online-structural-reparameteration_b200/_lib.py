@@ -67,6 +67,8 @@ _SIGNATURES = {
     "onr_stem_bwd_act": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
     "onr_stem_bwd_factors_act": (i32, [vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp]),
     "onr_act_map": (i32, [vp, vp, sz, i32, i32, i32, vp]),
+    "onr_add_bf16": (i32, [vp, vp, sz, vp]),
+    "onr_adaptive_avg_pool": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "onr_pos_encoding": (i32, [vp, i32, vp, i32, vp, vp]),
     "onr_frame_u8_to_f32": (i32, [vp, sz, vp, vp]),
     "onr_stem_bwd": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),

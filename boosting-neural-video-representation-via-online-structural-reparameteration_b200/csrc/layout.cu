@@ -69,9 +69,61 @@ __global__ void act_map_kernel(__nv_bfloat16* __restrict__ zy, __nv_bfloat16* __
     }
 }
 
+// dst += src over bf16 maps (fp32 add, one rounding): the gradient a multi-resolution head sends into a block output
+// joins the gradient the next block's dgrad has already written there (reference model.py:615-623 with sin_res=False).
+__global__ void add_bf16_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ src, size_t n_vec) {
+    for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < n_vec; v += (size_t)gridDim.x * blockDim.x) {
+        const uint4 a = reinterpret_cast<const uint4*>(dst)[v], b = __ldg(reinterpret_cast<const uint4*>(src) + v);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(bf16_lo(aw[e]) + bf16_lo(bw[e]), bf16_hi(aw[e]) + bf16_hi(bw[e]));
+        reinterpret_cast<uint4*>(dst)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// F.adaptive_avg_pool2d on NCHW fp32 planes (reference main_train.py:239: the frame pooled to each head's resolution):
+// output (oh, ow) averages rows [floor(oh*H/Ho), ceil((oh+1)*H/Ho)) x the same in w, summed in row-major order.
+__global__ void adaptive_avg_pool_kernel(const float* __restrict__ src, int planes, int H, int W, int Ho, int Wo,
+                                         float* __restrict__ dst) {
+    const size_t total = (size_t)planes * Ho * Wo;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int ow = (int)(idx % Wo);
+        const int oh = (int)((idx / Wo) % Ho);
+        const size_t pl = idx / ((size_t)Wo * Ho);
+        const int h0 = (int)(((long long)oh * H) / Ho), h1 = (int)((((long long)oh + 1) * H + Ho - 1) / Ho);
+        const int w0 = (int)(((long long)ow * W) / Wo), w1 = (int)((((long long)ow + 1) * W + Wo - 1) / Wo);
+        const float* p = src + pl * (size_t)H * W;
+        float acc = 0.0f;
+        for (int h = h0; h < h1; ++h)
+            for (int w = w0; w < w1; ++w) acc += p[(size_t)h * W + w];
+        dst[idx] = acc / (float)((h1 - h0) * (w1 - w0));
+    }
+}
+
 }  // namespace onr
 
 extern "C" {
+
+int onr_add_bf16(void* dst_bf16, const void* src_bf16, size_t n, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(dst_bf16 != nullptr && src_bf16 != nullptr && n % 8 == 0, "add_bf16: element count must be a multiple of 8");
+    if (n == 0) return 0;
+    add_bf16_kernel<<<layout_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<__nv_bfloat16*>(dst_bf16), reinterpret_cast<const __nv_bfloat16*>(src_bf16), n / 8);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
+
+int onr_adaptive_avg_pool(const float* src, int planes, int H, int W, int Ho, int Wo, float* dst, void* stream) {
+    using namespace onr;
+    ONR_REQUIRE(src != nullptr && dst != nullptr && planes >= 1 && H >= 1 && W >= 1 && Ho >= 1 && Wo >= 1,
+                "adaptive_avg_pool: bad shape");
+    adaptive_avg_pool_kernel<<<layout_grid((size_t)planes * Ho * Wo, 256), 256, 0, (cudaStream_t)stream>>>(
+        src, planes, H, W, Ho, Wo, dst);
+    ONR_LAUNCH_CHECK();
+    return 0;
+}
 
 int onr_act_map(void* zy_bf16, void* d_bf16, size_t pixels, int C, int Cp, int act, void* stream) {
     using namespace onr;

@@ -141,6 +141,16 @@ class NetExecutor:
         self.H, self.W, self.C_last = h, w, c
         L = len(self.geoms)
         self.L = L
+        # stages that carry an RGB head: the last one always; every stage with sin_res=False (reference
+        # model.py:598-608).  The head kernels keep the 3 x C weights in registers / shared memory: C <= 128 per stage.
+        self.head_stages = [l for l in range(L) if gen.head_layers[l] is not None]
+        assert self.head_stages and self.head_stages[-1] == L - 1
+        for l in self.head_stages:
+            if pad32(self.geoms[l].cnew) > 128:
+                raise NotImplementedError(
+                    f"RGB head on a stage of {self.geoms[l].cnew} channels: the head kernels take at most 128 "
+                    "(multi-resolution heads with wide early stages are outside the B200 hot path)")
+        self.multi = len(self.head_stages) > 1
 
         # ---- stem ------------------------------------------------------------------------------
         lin1, lin2 = gen.stem[0], gen.stem[2]
@@ -181,6 +191,11 @@ class NetExecutor:
             self.dz.append(zeros(B, hh, ww, cp, dtype=bf16) if train else None)
         self._img_static = zeros(B, 3, self.H, self.W)      # CUDA-graph paths always decode into this one
         self.img = self._img_static
+        # multi-resolution heads: image (and, in training, the head's dz contribution) of every earlier head stage
+        self._img_stage = {l: zeros(B, 3, self.geoms[l].ho, self.geoms[l].wo) for l in self.head_stages[:-1]}
+        self.imgs = dict(self._img_stage)
+        self._dz_head = ({l: zeros(B, self.geoms[l].ho, self.geoms[l].wo, self.geoms[l].cpo, dtype=bf16)
+                          for l in self.head_stages[:-1]} if train else {})
 
         # ---- per block weights / gradient staging ------------------------------------------------
         self.K, self.bias, self.T, self.wf, self.wd, self.bias_p = [], [], [], [], [], []
@@ -348,11 +363,14 @@ class NetExecutor:
               "onr_pack_weights")
 
     # ------------------------------------------------------------------------------------- forward
-    def forward(self, embed=None, t_norm=None, freqs=None, refresh=True, out=None):
+    def forward(self, embed=None, t_norm=None, freqs=None, refresh=True, out=None, outs=None):
         """Runs the decoder; returns the image [B,3,H,W] fp32: `out` when given (it then also becomes the image the
         next `backward` differentiates through), else the executor's own static buffer.
-        Either `embed` [B,2L] (reference entry) or `t_norm` [B] + `freqs` [L] (fused PE) is given."""
+        Either `embed` [B,2L] (reference entry) or `t_norm` [B] + `freqs` [L] (fused PE) is given.
+        With multi-resolution heads the images of the earlier stages land in `outs[l]` when given, else in static
+        buffers; `self.imgs` holds them either way."""
         self.img = out if out is not None else self._img_static
+        self.imgs = {l: (outs[l] if outs is not None else self._img_stage[l]) for l in self._img_stage}
         gen, st = self.gen, _lib.stream()
         lin1, lin2 = gen.stem[0], gen.stem[2]
         g0 = self.geoms[0]
@@ -395,6 +413,11 @@ class NetExecutor:
                 g = self.geoms[l]
                 check(self.lib.onr_act_map(ptr(self.x[l + 1]), ptr(self.d[l + 1]) if self.train else None,
                                            self.B * g.ho * g.wo, g.cnew, g.cpo, self.act, st), "onr_act_map")
+            if l in self.imgs:                                   # multi-resolution head of this stage
+                g, hl = self.geoms[l], gen.head_layers[l]
+                check(self.lib.onr_head_fwd(ptr(self.x[l + 1]), self.B, g.ho, g.wo, g.cnew, g.cpo, ptr(hl.weight),
+                                            ptr(hl.bias), 1 if gen.sigmoid else 0, ptr(self.imgs[l]), st),
+                      "onr_head_fwd(stage)")
         if self._decode_fused:
             return self.img
         head_fwd = self.lib.onr_head_fwd_z if self._last_z else self.lib.onr_head_fwd
@@ -409,17 +432,23 @@ class NetExecutor:
         the block convolutions and the head are captured once per set of packed weights — a 720p decode is eight
         kernels of 5-160 us, so the launch gaps of eager issue are a visible share of the frame.  Weights are re-folded /
         re-packed eagerly (outside the graph) whenever a parameter changed, which also drops the captured graph.
-        Returns a fresh image tensor, like the reference.  ONR_DECODE_GRAPH=0 keeps the eager launches."""
+        Returns fresh image tensors, like the reference: [image of every head stage ..., final image].
+        ONR_DECODE_GRAPH=0 keeps the eager launches."""
         assert not self.train
+
+        def snapshot():
+            return [self._img_stage[l].clone() for l in self.head_stages[:-1]] + [self._img_static.clone()]
+
         if os.environ.get("ONR_DECODE_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
             img = torch.empty(self.B, 3, self.H, self.W, dtype=torch.float32, device=self.dev)
-            self.forward(embed=embed, out=img)
-            return img
+            outs = {l: torch.empty_like(self._img_stage[l]) for l in self.head_stages[:-1]}
+            self.forward(embed=embed, out=img, outs=outs)
+            return [outs[l] for l in self.head_stages[:-1]] + [img]
         stale = self._weights_key() != getattr(self, "_packed_key", None)
         if stale or getattr(self, "_decode_graph", None) is None:
             self._decode_graph = None
             self.forward(embed=embed)                     # eager: refreshes the operands; the warm-up of the capture
-            out = self._img_static.clone()
+            out = snapshot()
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -428,10 +457,10 @@ class NetExecutor:
             return out
         self.embed.copy_(embed.reshape(self.B, self.E))
         self._decode_graph.replay()
-        return self._img_static.clone()
+        return snapshot()
 
     # ------------------------------------------------------------------------------------ backward
-    def backward(self, gimg, grads, block_hook=None, reduce=None):
+    def backward(self, gimg, grads, block_hook=None, reduce=None, gimgs=None):
         """Backward of `forward`. `grads` maps parameter name -> fp32 gradient tensor; every tensor must be
         zero on entry (the kernels accumulate into the ERB branch / stem / head gradients and overwrite the
         single-branch conv gradients).
@@ -441,6 +470,9 @@ class NetExecutor:
         head backward, each block's folded-kernel gradient `dK|dbias` right after its wgrad on the block's side stream
         (the linear fold backward then runs on the summed dK on every rank), stem gradients at the end — so the
         exchange overlaps the remaining dgrad chain.
+
+        gimgs, with multi-resolution heads: {stage l: dL/d(image of stage l)} for the earlier head stages; each head's
+        backward adds its contribution to dz[l+1] before block l's wgrad / dgrad consume it.
 
         block_hook(l), if given, is called on block l's side stream once that block's parameter gradients are
         complete AND its dgrad has been issued (nothing in this backward reads the block's weights, packed operands
@@ -509,6 +541,18 @@ class NetExecutor:
             main.wait_event(pool_clear)
         for l in reversed(range(self.L)):
             g, blk = self.geoms[l], gen.layers[l]
+            if gimgs is not None and l in self._dz_head and gimgs.get(l) is not None:
+                # head of an earlier stage (reference model.py:619-623 under autograd): its gradient w.r.t. the block
+                # output joins the one the next block's dgrad has just written into dz[l+1]
+                hl, nm = gen.head_layers[l], f"head_layers.{l}"
+                check(lib.onr_head_bwd(
+                    ptr(gimgs[l]), ptr(self.imgs[l]), ptr(self.x[l + 1]), ptr(self.d[l + 1]), self.B, g.ho, g.wo, g.cnew,
+                    g.cpo, ptr(hl.weight), 1 if gen.sigmoid else 0, ptr(grads[nm + ".weight"]), ptr(grads[nm + ".bias"]),
+                    ptr(self._dz_head[l]), st), "onr_head_bwd(stage)")
+                check(lib.onr_add_bf16(ptr(self.dz[l + 1]), ptr(self._dz_head[l]), self.dz[l + 1].numel(), st),
+                      "onr_add_bf16")
+                if reduce is not None:
+                    reduce(self._flat_span(grads, [nm + ".weight", nm + ".bias"]))
             # dz[l+1] is ready: wgrad -> un-pack -> fold backward of block l run on a side stream beside the
             # dgrad chain (only the dgrads and the stem backward are on the critical path)
             if not self._wgrad_on_side:

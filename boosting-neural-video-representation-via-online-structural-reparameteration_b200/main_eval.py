@@ -253,8 +253,8 @@ def decode_clip(model, pe, cache, args, log_path=None, local_rank=0, fwd_num=10,
                 vis = f'{args.outf}/visualize'
                 os.makedirs(vis, exist_ok=True)
                 save_image(out[-1][0], f'{vis}/pred_{i}.png')
-            psnrs.append(frame_stats(out[0], target)[4].view(1))
-            msssims.append(msssim_fn(out, [target]).view(1))
+            psnrs.append(frame_stats(out[-1], target)[4].view(1))   # the full-resolution stage
+            msssims.append(msssim_fn(out[-1:], [target]).view(1))
             if i % args.print_freq == 0 or i == len(cache) - 1:
                 fps = fwd_num * (i + 1) / sum(times)
                 print_str = 'Rank:{}, Step [{}/{}], PSNR: {}, MSSSIM: {} FPS: {}'.format(

@@ -57,8 +57,8 @@ def evaluate(model, cache, pe, args):
         torch.cuda.synchronize()
         t_fwd += time.time() - t0
         target = cache.frames[i:i + 1].float().div(255)
-        psnrs.append(frame_stats(out[0], target)[4].view(1))
-        msssims.append(msssim_fn(out, [target]).view(1))
+        psnrs.append(frame_stats(out[-1], target)[4].view(1))   # the full-resolution stage
+        msssims.append(msssim_fn(out[-1:], [target]).view(1))
     model.train()
     n = len(psnrs)
     return torch.cat(psnrs).mean().view(1), torch.cat(msssims).mean().view(1), n / max(t_fwd, 1e-9)
@@ -94,6 +94,47 @@ def fit_epoch(fitter, cache, args, epoch, total_epochs, spe, world, rank, local_
     return torch.stack(stats).mean(0).cpu()
 
 
+def fit_epoch_modules(model, pe, optimizer, cache, args, epoch, total_epochs, rank, local_rank, log_path=None):
+    """One epoch of the reference loop written against the drop-in MODULES (main_train.py:229-267 verbatim:
+    `model(embed)`, per-stage targets by adaptive average pooling, `loss_fn` per stage weighted by --lw,
+    `loss_sum.backward()`, `optimizer.step()`, `psnr_fn`, `msssim_fn`) — the path multi-resolution heads
+    (sin_res=False) train through; the single-resolution configurations use `FrameFitter` (fit_epoch) instead.
+    Single process.  Returns the epoch means (psnr[num_stage], msssim[num_stage]) as CPU tensors."""
+    from .utils import adaptive_avg_pool2d, adjust_lr, loss_fn, psnr_fn
+    device = next(model.parameters()).device
+    B, data_size = args.batchSize, len(cache)
+    perm = sharding.epoch_permutation(data_size, epoch, args.manualSeed)
+    n_steps = data_size // B if not args.debug else min(data_size // B, 11)
+    psnr_list, msssim_list = [], []
+    for i in range(n_steps):
+        idx = torch.tensor(perm[i * B:(i + 1) * B], device=device)
+        data = cache.frames[idx].float().div(255)
+        embed_input = pe(cache.t[idx])
+        output_list = model(embed_input)
+        target_list = [adaptive_avg_pool2d(data, x.shape[-2:]) for x in output_list]
+        loss_list = [loss_fn(output, target, args) for output, target in zip(output_list, target_list)]
+        loss_list = [loss_list[k] * (args.lw if k < len(loss_list) - 1 else 1) for k in range(len(loss_list))]
+        loss_sum = sum(loss_list)
+        lr = adjust_lr(optimizer, epoch % total_epochs, i, data_size, args)
+        optimizer.zero_grad()
+        loss_sum.backward()
+        optimizer.step()
+        with torch.no_grad():
+            psnr_list.append(psnr_fn(output_list, target_list))
+            msssim_list.append(msssim_fn(output_list, target_list))
+        if i % args.print_freq == 0 or i == n_steps - 1:
+            train_psnr = torch.cat(psnr_list, dim=0).mean(0).cpu()
+            train_msssim = torch.cat(msssim_list, dim=0).float().mean(0).cpu()
+            print_str = '[{}] Rank:{}, Epoch[{}/{}], Step [{}/{}], lr:{:.2e} PSNR: {}, MSSSIM: {}'.format(
+                datetime.now().strftime("%Y/%m/%d %H:%M:%S"), local_rank, epoch + 1, total_epochs, i + 1, n_steps,
+                lr, RoundTensor(train_psnr, 2, False), RoundTensor(train_msssim, 4, False))
+            print(print_str, flush=True)
+            if rank == 0 and log_path:
+                with open(log_path, 'a') as f:
+                    f.write(print_str + '\n')
+    return torch.cat(psnr_list, dim=0).mean(0).cpu(), torch.cat(msssim_list, dim=0).float().mean(0).cpu()
+
+
 def train(local_rank, rank, world, args):
     torch.manual_seed(args.manualSeed)
     np.random.seed(args.manualSeed)
@@ -120,22 +161,30 @@ def train(local_rank, rank, world, args):
     cache = FrameCache(args.dataset, device, vid_list=args.vid, frame_gap=args.frame_gap)
     data_size = len(cache)                                           # reference: len(train_dataset)
     spe = sharding.steps_per_epoch(data_size, world * args.batchSize)
-    fitter = FrameFitter(model, pe, args, optimizer=optimizer, world_size=world, steps_per_epoch=spe,
-                         data_size=data_size)
+    multi = not args.single_res
+    if multi and world > 1:
+        raise SystemExit('orepnerv: multi-resolution heads train through the module API in a single process (drop -d)')
+    fitter = None if multi else FrameFitter(model, pe, args, optimizer=optimizer, world_size=world,
+                                            steps_per_epoch=spe, data_size=data_size)
+    H_out, W_out = (int(x) for x in cache.frames.shape[-2:])
     start = datetime.now()
     for epoch in range(args.epochs):
         epoch_start = datetime.now()
-        st = fit_epoch(fitter, cache, args, epoch, args.epochs, spe, world, rank, local_rank, log_path)
-        train_psnr, train_msssim = st[4:5], st[5:6]
+        if multi:
+            train_psnr, train_msssim = fit_epoch_modules(model, pe, optimizer, cache, args, epoch, args.epochs, rank,
+                                                         local_rank, log_path)
+        else:
+            st = fit_epoch(fitter, cache, args, epoch, args.epochs, spe, world, rank, local_rank, log_path)
+            train_psnr, train_msssim = st[4:5], st[5:6]
         if rank == 0:
-            h, w = fitter.H, fitter.W
+            h, w = H_out, W_out
             is_train_best = bool(train_psnr[-1] > train_best_psnr)
             train_best_psnr = train_psnr[-1] if is_train_best else train_best_psnr
             train_best_msssim = train_msssim[-1] if train_msssim[-1] > train_best_msssim else train_best_msssim
             if writer is not None:
                 writer.add_scalar(f'Train/PSNR_{h}X{w}_gap{args.frame_gap}', train_psnr[-1].item(), epoch + 1)
                 writer.add_scalar(f'Train/MSSSIM_{h}X{w}_gap{args.frame_gap}', train_msssim[-1].item(), epoch + 1)
-                writer.add_scalar('Train/lr', fitter.opt.param_groups[0]['lr'], epoch + 1)
+                writer.add_scalar('Train/lr', optimizer.param_groups[0]['lr'], epoch + 1)
             now = datetime.now()
             print_str = '\t{}p: current: {:.2f}\t best: {:.2f}\t msssim_best: {:.4f}\t'.format(
                 h, train_psnr[-1].item(), float(train_best_psnr), float(train_best_msssim))
@@ -158,7 +207,7 @@ def train(local_rank, rank, world, args):
                 val_best_msssim = val_msssim[-1] if val_msssim[-1] > val_best_msssim else val_best_msssim
                 print_str = f'Eval best_PSNR at epoch{epoch + 1}:'
                 print_str += '\t{}p: current: {:.2f}\tbest: {:.2f} \tbest_msssim: {:.4f}\t decode fps: {:.1f}'.format(
-                    fitter.H, val_psnr[-1].item(), float(val_best_psnr), float(val_best_msssim), fps)
+                    H_out, val_psnr[-1].item(), float(val_best_psnr), float(val_best_msssim), fps)
                 print(print_str)
                 with open(log_path, 'a') as f:
                     f.write(print_str + '\n')

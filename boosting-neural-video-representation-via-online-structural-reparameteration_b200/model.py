@@ -329,13 +329,18 @@ class _GeneratorFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gen, ex, embed, *params):
         img = torch.empty(ex.B, 3, ex.H, ex.W, dtype=torch.float32, device=ex.dev)
-        ex.forward(embed=embed, out=img)
-        ctx.gen, ctx.ex = gen, ex
-        return img
+        early = ex.head_stages[:-1]                   # multi-resolution heads (sin_res=False): one image per stage
+        outs = {l: torch.empty(ex.B, 3, ex.geoms[l].ho, ex.geoms[l].wo, dtype=torch.float32, device=ex.dev)
+                for l in early}
+        ex.forward(embed=embed, out=img, outs=outs)
+        ctx.gen, ctx.ex, ctx.early = gen, ex, early
+        return tuple(outs[l] for l in early) + (img,)
 
     @staticmethod
-    def backward(ctx, gimg):
+    def backward(ctx, *gimgs_all):
         gen, ex = ctx.gen, ctx.ex
+        gimg = gimgs_all[-1]
+        gimgs = {l: g.contiguous() for l, g in zip(ctx.early, gimgs_all[:-1])} or None
         named = list(gen.named_parameters())
         pg = gen.persistent_grads()
         owned = [p.grad is pg[n] for n, p in named]
@@ -344,14 +349,14 @@ class _GeneratorFunction(torch.autograd.Function):
         if fast and (gen._grads_clean or not any(owned)):
             if not gen._grads_clean:
                 pg["__flat__"].zero_()
-            ex.backward(gimg.contiguous(), pg)
+            ex.backward(gimg.contiguous(), pg, gimgs=gimgs)
             gen._grads_clean = False
             for n, p in named:
                 if p.requires_grad:
                     p.grad = pg[n]
             return (None, None, None) + (None,) * len(named)
         grads = gen.alloc_grads()
-        ex.backward(gimg.contiguous(), grads)
+        ex.backward(gimg.contiguous(), grads, gimgs=gimgs)
         out = [grads[n] if p.requires_grad else None for n, p in named]
         return (None, None, None) + tuple(out)
 
@@ -367,7 +372,7 @@ class Generator(nn.Module):
         self.act_name = kargs.get('act', 'swish')
         _require(self.act_name in ACT_CODES, f"act {self.act_name!r}")
         _require(kargs.get('num_blocks', 1) == 1, "num_blocks > 1")
-        _require(bool(kargs.get('sin_res', True)), "multi-resolution heads (sin_res=False)")
+        self.sin_res = bool(kargs.get('sin_res', True))
         _require(kargs.get('bias', True), "bias=False")
         # reference MLP(): Linear, act, Linear, act with one shared activation module (model.py:184-188)
         act_fn = activation_module(self.act_name)
@@ -388,8 +393,9 @@ class Generator(nn.Module):
                                          conv_type=kargs.get('conv_type', 'conv'),
                                          branch_type=kargs['branch_type']))
             ngf = new_ngf
+            # reference model.py:598-608: one RGB head on the last stage (sin_res) or on every stage
             self.head_layers.append(nn.Conv2d(ngf, 3, 1, 1, bias=kargs['bias'])
-                                    if i == len(strides) - 1 else None)
+                                    if (i == len(strides) - 1 or not self.sin_res) else None)
         self.sigmoid = kargs['sigmoid']
         self._executors = {}
         self._pgrads = None
@@ -465,14 +471,13 @@ class Generator(nn.Module):
         return new
 
     def forward(self, input):
-        """input: embedding [B, 2*levels] (reference model.py:611-625). Returns [img[B,3,H,W]]."""
+        """input: embedding [B, 2*levels] (reference model.py:611-625). Returns the list of images, one per head
+        stage ([img[B,3,H,W]] with sin_res)."""
         B = input.size(0)
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         ex = self.executor(B, needs_grad)
         if needs_grad:
             params = [p for _, p in self.named_parameters()]
-            img = _GeneratorFunction.apply(self, ex, input.detach(), *params)
-        else:
-            with torch.no_grad():
-                img = ex.decode(input)
-        return [img]
+            return list(_GeneratorFunction.apply(self, ex, input.detach(), *params))
+        with torch.no_grad():
+            return ex.decode(input)

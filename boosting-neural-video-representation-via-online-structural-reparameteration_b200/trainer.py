@@ -67,6 +67,9 @@ class FrameFitter:
             raise NotImplementedError(f"loss_type {args.loss_type!r} is outside the B200 hot path")
         self.w_l1, self.w_mse, self.w_ssim = LOSS_TERMS[args.loss_type]
         self.ex = model.executor(self.B, True)
+        if self.ex.multi:
+            raise NotImplementedError("FrameFitter fits the single-resolution head; multi-resolution heads "
+                                      "(sin_res=False) train through the module API (main_train does that)")
         dev = self.ex.dev
         self.dev = dev
         H, W = self.ex.H, self.ex.W

@@ -141,6 +141,20 @@ def loss_fn(pred, target, args):
     return loss
 
 
+def adaptive_avg_pool2d(data, size):
+    """F.adaptive_avg_pool2d(data, size) on the device (reference main_train.py:239: the frame pooled to the
+    resolution of each head).  The identity when the size already matches (the single-resolution case)."""
+    Ho, Wo = int(size[0]), int(size[1])
+    if tuple(data.shape[-2:]) == (Ho, Wo):
+        return data
+    x = _cuda_f32(data)
+    B, C, H, W = x.shape
+    out = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device=x.device)
+    check(_lib.lib().onr_adaptive_avg_pool(ptr(x), B * C, H, W, Ho, Wo, ptr(out), _lib.stream()),
+          "onr_adaptive_avg_pool")
+    return out
+
+
 def frame_stats(pred, target):
     """out5 = [Fusion6 loss, L1, SSIM, MSE, PSNR] of a [B,3,H,W] pair, no gradient."""
     lib = _lib.lib()

@@ -238,6 +238,15 @@ int onr_nhwc_bf16_to_nchw(const void* src, int B, int C, int H, int W, int Cp, f
  * kernel turns z[pixels][Cp] (NHWC bf16) into y = act(z) IN PLACE and d = act'(z) (d may be NULL: decode). */
 int onr_act_map(void* zy_bf16, void* d_bf16, size_t pixels, int C, int Cp, int act, void* stream);
 
+/* ------------------------------------------------------------------ multi-resolution heads (8f-4; sin_res=False)
+ * model.py:598-608, :615-623: a 1x1 RGB head on EVERY stage; main_train.py:239-244: the frame is pooled to each head's
+ * resolution (F.adaptive_avg_pool2d) and the per-stage losses are summed with weight --lw for all but the last.
+ * The per-stage heads reuse onr_head_fwd / onr_head_bwd; the two helpers below are what is new:
+ * dst += src over n bf16 elements (n % 8 == 0) — the head's gradient joins the dgrad output of the next block; and
+ * adaptive average pooling of NCHW fp32 planes [planes][H][W] -> [planes][Ho][Wo] (PyTorch's window rule). */
+int onr_add_bf16(void* dst_bf16, const void* src_bf16, size_t n, void* stream);
+int onr_adaptive_avg_pool(const float* src, int planes, int H, int W, int Ho, int Wo, float* dst, void* stream);
+
 /* ------------------------------------------------------------------ A6: RGB head
  * model.py:601, :620-623: 1x1 conv C->3 + bias, then (tanh+1)/2 or sigmoid.
  * y NHWC bf16 [B][H][W][Cp] -> img NCHW fp32 [B][3][H][W]. */

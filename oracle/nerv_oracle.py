@@ -200,6 +200,24 @@ def generator_forward(sd, embed, cfg, return_features=False):
     return (img, feats) if return_features else img
 
 
+def generator_forward_multi(sd, embed, cfg):
+    """reference model.py:611-625 with sin_res=False: the image of EVERY stage that owns a head (`head_layers.i.*`
+    present in the state dict), in stage order."""
+    _, feats = generator_forward(sd, embed, cfg, return_features=True)
+    return [head_forward(feats[i + 1], sd[f'head_layers.{i}.weight'], sd[f'head_layers.{i}.bias'], cfg.get('sigmoid', False))
+            for i in range(len(cfg['strides'])) if f'head_layers.{i}.weight' in sd]
+
+
+def multires_loss(sd, embed, data, cfg, lw, loss_type='Fusion6'):
+    """reference main_train.py:238-244: per-stage targets by adaptive average pooling, per-stage losses, weight `lw` on
+    all but the last.  Returns (loss_sum, images, targets)."""
+    imgs = generator_forward_multi(sd, embed, cfg)
+    targets = [F.adaptive_avg_pool2d(data, x.shape[-2:]) for x in imgs]
+    losses = [loss_fn(o, t, loss_type) for o, t in zip(imgs, targets)]
+    losses = [l * (lw if i < len(losses) - 1 else 1) for i, l in enumerate(losses)]
+    return sum(losses), imgs, targets
+
+
 # ----------------------------------------------------------------------------- A7/A10 SSIM family
 def _gauss_1d(size=11, sigma=1.5, dtype=torch.float32):
     """pytorch_msssim 0.2.1 `_fspecial_gauss_1d`."""

@@ -210,8 +210,67 @@ def finetune_case(branch_type, src, name, amount=0.3, start_epoch=3, finetune_ep
     print(name, 'losses', losses, 'lrs', lrs, 'max |effective weight - pruned start|', moved)
 
 
+MULTI = dict(embed='1.25_40', stem_dim_num='64_1', fc_hw_dim='4_6_12', expansion=1, reduction=2, lower_width=8,
+             strides=[3, 2])
+
+
+def multires_case(name, lw=0.7, n_steps=3):
+    """Multi-resolution heads (sin_res=False, reference model.py:598-608, :615-623) through the reference's own
+    training iteration (main_train.py:238-250): one RGB head per stage, the frame pooled to every head's resolution,
+    per-stage Fusion6 losses summed with weight --lw on all but the last."""
+    import torch.nn.functional as F
+    cfg = MULTI
+    torch.manual_seed(1)
+    pe = ref_utils.PositionalEncoding(cfg['embed'])
+    gen = ref_model.Generator(embed_length=pe.embed_length, stem_dim_num=cfg['stem_dim_num'], fc_hw_dim=cfg['fc_hw_dim'],
+                              expansion=cfg['expansion'], num_blocks=1, norm='none', act='swish', bias=True,
+                              reduction=cfg['reduction'], conv_type='conv', stride_list=cfg['strides'], sin_res=False,
+                              lower_width=cfg['lower_width'], sigmoid=False, deploy=False, branch_type='ERB')
+    out = {'cfg': cfg, 'lw': lw, 'init_state': {k: v.clone() for k, v in gen.state_dict().items()}}
+    pos = torch.tensor([0.25, 0.7])
+    embed = pe(pos)
+    out['pos'], out['embed'] = pos, embed.clone()
+    args = argparse.Namespace(loss_type='Fusion6', lr=5e-4, lr_type='cosine', warmup=1, epochs=5, lw=lw)
+
+    def step_loss(data):
+        output_list = gen(embed)
+        target_list = [F.adaptive_avg_pool2d(data, x.shape[-2:]) for x in output_list]
+        loss_list = [ref_utils.loss_fn(o, t, args) for o, t in zip(output_list, target_list)]
+        loss_list = [loss_list[i] * (args.lw if i < len(loss_list) - 1 else 1) for i in range(len(loss_list))]
+        return output_list, target_list, loss_list, sum(loss_list)
+
+    imgs = gen(embed)
+    H, W = imgs[-1].shape[-2:]
+    data = frames(2, H, W, 7)
+    out['target'] = data
+    output_list, target_list, loss_list, loss_sum = step_loss(data)
+    out['imgs'] = [o.detach().clone() for o in output_list]
+    out['targets'] = [t.clone() for t in target_list]
+    out['losses'] = [l.detach().clone() for l in loss_list]
+    out['loss_sum'] = loss_sum.detach().clone()
+    gen.zero_grad()
+    loss_sum.backward()
+    out['grads'] = {k: p.grad.detach().clone() for k, p in gen.named_parameters()}
+    out['psnr'] = ref_utils.psnr_fn([o.detach() for o in output_list], target_list).clone()
+    opt = torch.optim.Adam(gen.parameters(), betas=(0.5, 0.999))
+    losses = []
+    for i in range(n_steps):
+        _, _, _, l = step_loss(data)
+        ref_utils.adjust_lr(opt, 0, i, 4, args)
+        opt.zero_grad()
+        l.backward()
+        opt.step()
+        losses.append(l.item())
+    out['train_losses'] = losses
+    out['trained_state'] = {k: v.clone() for k, v in gen.state_dict().items()}
+    torch.save(out, os.path.join(HERE, name))
+    print(name, [tuple(o.shape) for o in output_list], 'loss', float(loss_sum.detach()), losses)
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['base']
+    if 'multires' in what:
+        multires_case('small_erb_multires.pt')
     if 'base' in what:
         case(TINY, 'ERB', 'tiny_erb.pt')
         case(TINY, 'NeRV_vanilla', 'tiny_vanilla.pt')

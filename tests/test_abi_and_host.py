@@ -93,7 +93,7 @@ def test_deepcopy_drops_executors(golden):
 
 
 @pytest.mark.parametrize("kw", [dict(branch_type='OREPA'), dict(act='mish'), dict(norm='bn'), dict(num_blocks=2),
-                                dict(sin_res=False)])
+                                dict(stem_dim_num='16_2')])
 def test_out_of_scope_configs_raise(kw):
     base = dict(embed_length=8, stem_dim_num='16_1', fc_hw_dim='3_4_4', expansion=1, num_blocks=1, norm='none',
                 act='swish', bias=True, reduction=2, conv_type='conv', stride_list=[2, 2], sin_res=True,

@@ -171,3 +171,34 @@ def test_train_state_prune_list_order():
         'layers.0.rbr_1x1_3x3_1x1_branch_1x1_2'] and len(erb) == 14
     van = [n for n, _ in train_state_prunable(Generator(branch_type='NeRV_vanilla', **kw))]
     assert van == ['stem.0', 'stem.2', 'layers.0.branch', 'layers.1.branch']
+
+
+# ------------------------------------------------------------------------------------------- multi-resolution heads
+def test_oracle_multires_matches_reference(golden):
+    g = golden("small_erb_multires.pt")
+    cfg = cfg_of(g)
+    params = {k: v.clone().requires_grad_(True) for k, v in g['init_state'].items()}
+    loss, imgs, targets = O.multires_loss(params, g['embed'], g['target'], cfg, g['lw'])
+    assert len(imgs) == len(g['imgs']) == 2
+    for a, b in zip(imgs, g['imgs']):
+        torch.testing.assert_close(a.detach(), b, rtol=1e-5, atol=1e-6)
+    for a, b in zip(targets, g['targets']):
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-7)
+    torch.testing.assert_close(loss.detach(), g['loss_sum'], rtol=1e-5, atol=1e-6)
+    for (k, p), gr in zip(params.items(), torch.autograd.grad(loss, list(params.values()))):
+        torch.testing.assert_close(gr, g['grads'][k], rtol=5e-4, atol=2e-7, msg=lambda m: f"{k}: {m}")
+
+
+def test_generator_multires_layout(golden):
+    """sin_res=False: a head on every stage, same state-dict keys and initial values as the reference."""
+    from orepnerv.model import Generator
+    g = golden("small_erb_multires.pt")
+    c = g['cfg']
+    torch.manual_seed(1)
+    gen = Generator(embed_length=80, stem_dim_num=c['stem_dim_num'], fc_hw_dim=c['fc_hw_dim'], expansion=c['expansion'],
+                    num_blocks=1, norm='none', act='swish', bias=True, reduction=c['reduction'], conv_type='conv',
+                    stride_list=c['strides'], sin_res=False, lower_width=c['lower_width'], sigmoid=False, deploy=False,
+                    branch_type='ERB')
+    sd = gen.state_dict()
+    assert list(sd) == list(g['init_state'])
+    assert all(torch.equal(sd[k], v) for k, v in g['init_state'].items())

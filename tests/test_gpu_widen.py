@@ -371,3 +371,112 @@ def test_decode_graph_matches_eager(dev, golden, monkeypatch):
         assert torch.equal(changed, dep(embeds[0])[0])
         monkeypatch.delenv("ONR_DECODE_GRAPH")
         assert torch.equal(changed, dep(embeds[0])[0])           # replay of the re-captured graph
+
+
+# ------------------------------------------------------------------------------------------- multi-resolution heads
+def test_multires_heads_against_reference_golden(dev, golden):
+    """sin_res=False (reference model.py:598-608, main_train.py:238-250): one image per stage, per-stage pooled targets,
+    lw-weighted loss sum, every gradient — against the reference's own run; then three optimisation steps of the module
+    loop (main_train.fit_epoch_modules' body) against the reference's losses."""
+    from orepnerv.model import Generator
+    from orepnerv.optim import FusedAdam
+    from orepnerv.utils import PositionalEncoding, adaptive_avg_pool2d, adjust_lr, loss_fn, psnr_fn
+    g = golden("small_erb_multires.pt")
+    c, lw = g['cfg'], g['lw']
+    torch.manual_seed(1)
+    pe = PositionalEncoding(c['embed'])
+    gen = Generator(embed_length=pe.embed_length, stem_dim_num=c['stem_dim_num'], fc_hw_dim=c['fc_hw_dim'],
+                    expansion=c['expansion'], num_blocks=1, norm='none', act='swish', bias=True,
+                    reduction=c['reduction'], conv_type='conv', stride_list=c['strides'], sin_res=False,
+                    lower_width=c['lower_width'], sigmoid=False, deploy=False, branch_type='ERB').to(dev)
+    args = argparse.Namespace(loss_type='Fusion6', lr=5e-4, lr_type='cosine', warmup=1, epochs=5, lw=lw)
+    data = g['target'].to(dev)
+    embed = pe(g['pos'])
+
+    def step_loss():
+        output_list = gen(embed)
+        target_list = [adaptive_avg_pool2d(data, x.shape[-2:]) for x in output_list]
+        loss_list = [loss_fn(o, t, args) for o, t in zip(output_list, target_list)]
+        loss_list = [loss_list[i] * (args.lw if i < len(loss_list) - 1 else 1) for i in range(len(loss_list))]
+        return output_list, target_list, sum(loss_list)
+
+    output_list, target_list, loss_sum = step_loss()
+    assert [tuple(o.shape) for o in output_list] == [tuple(o.shape) for o in g['imgs']]
+    for a, b in zip(output_list, g['imgs']):
+        assert rel_l2(a, b) <= 1e-2
+    for a, b in zip(target_list, g['targets']):
+        assert (a.cpu() - b).abs().max().item() <= 1e-6
+    assert abs(loss_sum.item() - g['loss_sum'].item()) <= 3e-3
+    loss_sum.backward()
+    for k, p in gen.named_parameters():
+        ref = g['grads'][k]
+        err = (p.grad.cpu() - ref).norm().item()
+        assert err <= 3e-2 * ref.norm().item() + 1e-6, (k, err, ref.norm().item())
+    psnr = psnr_fn([o.detach() for o in output_list], target_list)
+    assert (psnr.cpu() - g['psnr']).abs().max().item() <= 0.05
+    opt = FusedAdam(gen.parameters(), betas=(0.5, 0.999))
+    for p in gen.parameters():
+        p.grad = None
+    for i, loss_ref in enumerate(g['train_losses']):
+        _, _, l = step_loss()
+        adjust_lr(opt, 0, i, 4, args)
+        opt.zero_grad()
+        l.backward()
+        opt.step()
+        assert abs(l.item() - loss_ref) <= 3e-3, (i, l.item(), loss_ref)
+    sd = gen.state_dict()
+    for k, v in g['trained_state'].items():
+        moved_ref = v - g['init_state'][k]
+        assert ((sd[k].cpu() - g['init_state'][k]) - moved_ref).norm().item() <= 0.35 * moved_ref.norm().item() + 1e-7, k
+    # decode: a list with one fresh image per stage, graph replay == eager
+    gen.eval()
+    with torch.no_grad():
+        a = gen(embed)
+        b = gen(embed)
+    assert len(a) == 2 and all(torch.equal(x, y) and x.data_ptr() != y.data_ptr() for x, y in zip(a, b))
+
+
+def test_adaptive_avg_pool_kernel(dev):
+    import torch.nn.functional as F
+    from orepnerv.utils import adaptive_avg_pool2d
+    x = torch.rand(2, 3, 37, 53, generator=torch.Generator().manual_seed(2))
+    for size in [(37, 53), (18, 26), (9, 16), (5, 53), (1, 1), (12, 18)]:
+        out = adaptive_avg_pool2d(x.to(dev), size)
+        torch.testing.assert_close(out.cpu(), F.adaptive_avg_pool2d(x, size), rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------- the reference's default flags
+def test_reference_default_architecture_full_size(dev):
+    """The reference CLI defaults (main_train.py:39-109): NeRV_vanilla, --act gelu, --loss_type L2, --embed 1.25_80,
+    --stem_dim_num 1024_1, --fc_hw_dim 9_16_128, --expansion 8, --lower_width 32, --strides 5 3 2 2 2 (1080p), with
+    --single_res: block inputs of 128 / 1024 / 512 / 256 / 128 channels (wgrad in up to 8 channel chunks), N = 25 600 on
+    block 0.  One full-size frame: image, loss and every parameter gradient against the fp32 GPU oracle."""
+    import fullsize_util as U
+    from orepnerv.data import synthetic_clip
+    from orepnerv.utils import loss_fn
+    cfg = dict(embed='1.25_80', stem_dim_num='1024_1', fc_hw_dim='9_16_128', expansion=8, reduction=2, lower_width=32,
+               strides=[5, 3, 2, 2, 2])
+    pe, gen = build(cfg, "NeRV_vanilla", dev, act='gelu')
+    pos = torch.tensor([5 / 132])
+    target = synthetic_clip(6, 1080, 1920, device=dev)[5:6].float().div(255)
+    img = gen(pe(pos))[0]
+    assert tuple(img.shape) == (1, 3, 1080, 1920)
+    loss = loss_fn(img, target, argparse.Namespace(loss_type='L2'))
+    loss.backward()
+    torch.cuda.synchronize()
+    with U.fp32_oracle_math():
+        params = {k: v.detach().clone().requires_grad_(True) for k, v in gen.state_dict().items()}
+        embed = O.pos_encoding(pos, 1.25, 80).to(dev)
+        img_ref = O.generator_forward(params, embed, ocfg(cfg, 'gelu'))
+        loss_ref = O.loss_fn(img_ref, target, 'L2')
+        grads_ref = torch.autograd.grad(loss_ref, list(params.values()))
+    res = {"config": "reference defaults, single_res, 1080p", "img_rel_l2": rel_l2(img, img_ref),
+           "loss": loss.item(), "loss_ref": loss_ref.item()}
+    named = dict(gen.named_parameters())
+    gerr = {k: (named[k].grad - gr).norm().item() / (gr.norm().item() + 1e-30) for (k, _), gr in zip(params.items(), grads_ref)}
+    res["grad_rel_l2_max"], res["grad_rel_l2_worst"] = max(gerr.values()), max(gerr, key=gerr.get)
+    U.record("reference_defaults", res)
+    print(res)
+    assert res["img_rel_l2"] <= 2e-3, res
+    assert abs(res["loss"] - res["loss_ref"]) <= 1e-4, res
+    assert res["grad_rel_l2_max"] <= 3e-2, res
