@@ -85,7 +85,7 @@ def build_parser(eval_mode=False):
 SUPPORTED = ("supported on the B200 hot path: --branch_type NeRV_vanilla|ERB (the north-star path) and ACB|RepVGG|DBB|ECB "
              "(folded online into one convolution like ERB), every --act (swish is fused into the convolution, the "
              "others take one extra elementwise pass), --norm none, --single_res (multi-resolution heads with --lw run through "
-             "the module API when every stage has at most 128 channels), "
+             "the module API), "
              "--num_blocks 1, --stem_dim_num <dim>_1, --conv_type conv, --loss_type L2|L1|SSIM|Fusion1..Fusion9, "
              "--lr_type cosine|const|step, --finetune with --prune_ratio < 1 (NeRV_vanilla|ERB); README recipe: --embed 1.25_40 "
              "--stem_dim_num 512_1 --fc_hw_dim 9_16_26 --expansion 1 --reduction 2 --lower_width 96 --strides 5 2 2 2 2 "
@@ -108,16 +108,17 @@ def validate_args(args):
     if args.norm != 'none':
         bad.append(f'--norm {args.norm}')
     if not args.single_res:
-        # multi-resolution heads (model.py:598-608) reuse the streaming head kernels: at most 128 channels per stage
+        # multi-resolution heads (model.py:598-608): streaming head kernels up to 128 channels, plain wide-head kernels
+        # up to 1024 on the earlier stages
         try:
             width, wide = int(str(args.fc_hw_dim).split('_')[2]), []
             for i, s_ in enumerate(args.strides):
                 width = int(width * args.expansion) if i == 0 else max(width // (1 if s_ == 1 else args.reduction),
                                                                          args.lower_width)
                 wide.append(width)
-            if max(wide) > 128:
-                bad.append(f'multi-resolution heads on stages of {max(wide)} channels (at most 128 per stage: pass '
-                           '--single_res, or widths like --fc_hw_dim 9_16_26 --expansion 1 --lower_width 96)')
+            if max(wide) > 1024 or wide[-1] > 128:
+                bad.append(f'multi-resolution heads on stages of {max(wide)} channels (at most 1024 per early stage, '
+                           '128 on the last)')
         except (IndexError, ValueError):
             pass
     if args.num_blocks != 1:

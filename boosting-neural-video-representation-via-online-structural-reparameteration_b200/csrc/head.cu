@@ -536,6 +536,95 @@ __global__ void __launch_bounds__(32 + kHfConsumers, 1) head_fwd_stream_kernel(c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Wide heads (more than kHeadMaxC channels): the multi-resolution heads of wide early stages (sin_res=False with the
+// reference's default widths: 1024 / 512 / 256 channels on 45x80 .. 270x480 maps, model.py:598-608).  Small maps off
+// the north-star path: plain kernels, one warp per pixel with the lanes striding over the channels.
+__global__ void head_wide_fwd_kernel(const __nv_bfloat16* __restrict__ y, uint32_t npix, uint32_t HW, int C, int Cp,
+                                     const float* __restrict__ Wh, const float* __restrict__ bh, int use_sigmoid,
+                                     float* __restrict__ img) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += warps) {
+        const __nv_bfloat16* row = y + (size_t)pix * Cp;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+        for (int c = lane; c < C; c += 32) {
+            const float v = __bfloat162float(row[c]);
+            a0 = fmaf(v, __ldg(Wh + c), a0);
+            a1 = fmaf(v, __ldg(Wh + C + c), a1);
+            a2 = fmaf(v, __ldg(Wh + 2 * C + c), a2);
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        if (lane < 3) {
+            const float a = (lane == 0 ? a0 : (lane == 1 ? a1 : a2)) + __ldg(bh + lane);
+            const uint32_t b = pix / HW;
+            img[(size_t)b * 3u * HW + (size_t)lane * HW + (pix - b * HW)] = head_act(a, use_sigmoid);
+        }
+    }
+}
+
+// dz[p,c] = (sum_k Wh[k,c] gpre[p,k]) * d[p,c];  gWh[k,c] += sum_p gpre[p,k] y[p,c];  gbh[k] += sum_p gpre[p,k].
+// A block owns a run of pixels; thread t owns channels t, t + blockDim, ...: its weight-gradient partials stay in
+// registers over the run (3 per owned channel, at most kWideOwn channels) and are combined with atomics at the end.
+constexpr int kWideOwn = 4;              // channels per thread: C <= kWideOwn * 256
+__global__ void __launch_bounds__(256)
+head_wide_bwd_kernel(const float* __restrict__ gimg, const float* __restrict__ img, const __nv_bfloat16* __restrict__ y,
+                     const __nv_bfloat16* __restrict__ dact, uint32_t npix, uint32_t HW, int C, int Cp,
+                     const float* __restrict__ Wh, int use_sigmoid, float* __restrict__ gWh, float* __restrict__ gbh,
+                     __nv_bfloat16* __restrict__ dz, uint32_t px_per_block) {
+    __shared__ float sgp[3];
+    const uint32_t p0 = blockIdx.x * px_per_block;
+    const uint32_t p1 = min(npix, p0 + px_per_block);
+    float w[kWideOwn][3], acc[kWideOwn][3], gb[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int j = 0; j < kWideOwn; ++j) {
+        const int c = threadIdx.x + j * 256;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            w[j][k] = c < C ? __ldg(Wh + k * C + c) : 0.0f;
+            acc[j][k] = 0.0f;
+        }
+    }
+    for (uint32_t pix = p0; pix < p1; ++pix) {
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            const uint32_t b = pix / HW;
+            const size_t o = (size_t)b * 3u * HW + (size_t)threadIdx.x * HW + (pix - b * HW);
+            const float g = gimg[o], v = img[o];
+            sgp[threadIdx.x] = use_sigmoid ? g * v * (1.0f - v) : g * 2.0f * v * (1.0f - v);
+        }
+        __syncthreads();
+        const float g0 = sgp[0], g1 = sgp[1], g2 = sgp[2];
+        if (threadIdx.x == 0) { gb[0] += g0; gb[1] += g1; gb[2] += g2; }
+#pragma unroll
+        for (int j = 0; j < kWideOwn; ++j) {
+            const int c = threadIdx.x + j * 256;
+            if (c < Cp) {
+                const size_t o = (size_t)pix * Cp + c;
+                float out = 0.0f;
+                if (c < C) {
+                    const float yv = __bfloat162float(y[o]);
+                    acc[j][0] = fmaf(g0, yv, acc[j][0]);
+                    acc[j][1] = fmaf(g1, yv, acc[j][1]);
+                    acc[j][2] = fmaf(g2, yv, acc[j][2]);
+                    out = (w[j][0] * g0 + w[j][1] * g1 + w[j][2] * g2) * __bfloat162float(dact[o]);
+                }
+                dz[o] = __float2bfloat16(out);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kWideOwn; ++j) {
+        const int c = threadIdx.x + j * 256;
+        if (c < C)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) atomicAdd(gWh + k * C + c, acc[j][k]);
+    }
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) atomicAdd(gbh + k, gb[k]);
+}
+
 // threads per block: a multiple of `chunks` close to `target`, holding whole pixels
 static inline int head_threads(int chunks, int target) { return (target / chunks) * chunks; }
 static inline bool head_fits_u32(size_t npix, int chunks) { return npix * (size_t)chunks * 3 < (1ull << 31); }
@@ -607,8 +696,17 @@ int onr_head_fwd_z(const void* z, int B, int H, int W, int C, int Cp, const floa
 int onr_head_fwd(const void* y, int B, int H, int W, int C, int Cp, const float* Wh, const float* bh,
                  int use_sigmoid, float* img, void* stream) {
     using namespace onr;
-    ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
     const size_t npix = (size_t)B * H * W;
+    if (Cp > kHeadMaxC) {                       // wide head of an early multi-resolution stage
+        ONR_REQUIRE(Cp % 32 == 0 && C <= Cp && npix < (1ull << 31), "head: unsupported shape");
+        size_t grid = (npix * 32 + 255) / 256;
+        if (grid > (size_t)num_sms() * 8) grid = (size_t)num_sms() * 8;
+        head_wide_fwd_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const __nv_bfloat16*>(y), (uint32_t)npix, (uint32_t)(H * W), C, Cp, Wh, bh, use_sigmoid, img);
+        ONR_LAUNCH_CHECK();
+        return 0;
+    }
+    ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
     const int chunks = Cp / 8;
     ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
     static const bool no_stream = getenv("ONR_HEAD_STREAM") && atoi(getenv("ONR_HEAD_STREAM")) == 0;
@@ -676,8 +774,20 @@ int onr_head_bwd(const float* gimg, const float* img, const void* y, const void*
                  int C, int Cp, const float* Wh, int use_sigmoid, float* gWh, float* gbh, void* dz,
                  void* stream) {
     using namespace onr;
-    ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
     const size_t npix = (size_t)B * H * W;
+    if (Cp > kHeadMaxC) {                       // wide head of an early multi-resolution stage
+        ONR_REQUIRE(Cp % 32 == 0 && C <= Cp && Cp <= kWideOwn * 256 && npix < (1ull << 31),
+                    "head: at most %d channels", kWideOwn * 256);
+        uint32_t ppb = (uint32_t)((npix + (size_t)num_sms() * 4 - 1) / ((size_t)num_sms() * 4));
+        if (ppb < 8) ppb = 8;
+        const int grid = (int)((npix + ppb - 1) / ppb);
+        head_wide_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            gimg, img, reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dsilu),
+            (uint32_t)npix, (uint32_t)(H * W), C, Cp, Wh, use_sigmoid, gWh, gbh, reinterpret_cast<__nv_bfloat16*>(dz), ppb);
+        ONR_LAUNCH_CHECK();
+        return 0;
+    }
+    ONR_REQUIRE(Cp % 32 == 0 && Cp <= kHeadMaxC && C <= Cp, "head: unsupported channels");
     const int chunks = Cp / 8;
     ONR_REQUIRE(head_fits_u32(npix, chunks), "head: too many pixels for 32-bit indexing");
     static const bool no_stream = getenv("ONR_HEAD_STREAM") && atoi(getenv("ONR_HEAD_STREAM")) == 0;

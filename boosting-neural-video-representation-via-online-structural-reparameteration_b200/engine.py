@@ -145,11 +145,13 @@ class NetExecutor:
         # model.py:598-608).  The head kernels keep the 3 x C weights in registers / shared memory: C <= 128 per stage.
         self.head_stages = [l for l in range(L) if gen.head_layers[l] is not None]
         assert self.head_stages and self.head_stages[-1] == L - 1
+        # (wider early stages — sin_res=False with the reference's default widths — take the plain wide-head kernels,
+        # at most 1024 channels)
         for l in self.head_stages:
-            if pad32(self.geoms[l].cnew) > 128:
+            limit = 128 if l == L - 1 else 1024
+            if pad32(self.geoms[l].cnew) > limit:
                 raise NotImplementedError(
-                    f"RGB head on a stage of {self.geoms[l].cnew} channels: the head kernels take at most 128 "
-                    "(multi-resolution heads with wide early stages are outside the B200 hot path)")
+                    f"RGB head on a stage of {self.geoms[l].cnew} channels: the head kernels take at most {limit} here")
         self.multi = len(self.head_stages) > 1
 
         # ---- stem ------------------------------------------------------------------------------

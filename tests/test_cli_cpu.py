@@ -144,8 +144,9 @@ def test_cli_accepts_the_widened_rows_and_rejects_the_rest():
             finish_args(build_parser().parse_args(base + extra))
     no_single = [a for a in base if a != '--single_res']
     assert not finish_args(build_parser().parse_args(no_single + ['--lw', '0.5'])).single_res   # <= 128 channels per stage
-    with pytest.raises(SystemExit):                                         # heads on 1024-channel stages
-        finish_args(build_parser().parse_args(no_single + ['--fc_hw_dim', '9_16_128', '--expansion', '8']))
+    finish_args(build_parser().parse_args(no_single + ['--fc_hw_dim', '9_16_128', '--expansion', '8']))   # wide-head kernels
+    with pytest.raises(SystemExit):                                         # a head on a 2048-channel stage
+        finish_args(build_parser().parse_args(no_single + ['--fc_hw_dim', '9_16_128', '--expansion', '16']))
     with pytest.raises(SystemExit):                                         # the reference finetunes NeRV_vanilla | ERB only
         finish_args(build_parser(eval_mode=True).parse_args(base + ['--branch_type', 'DBB', '--prune_ratio', '0.4',
                                                                     '--finetune']))

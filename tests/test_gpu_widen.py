@@ -480,3 +480,37 @@ def test_reference_default_architecture_full_size(dev):
     assert res["img_rel_l2"] <= 2e-3, res
     assert abs(res["loss"] - res["loss_ref"]) <= 1e-4, res
     assert res["grad_rel_l2_max"] <= 3e-2, res
+
+
+def test_multires_wide_early_stage(dev):
+    """sin_res=False with an early stage wider than 128 channels (the reference's default widths put 1024 / 512 / 256
+    channels under the early heads): the plain wide-head kernels, against the oracle on the same parameters."""
+    from orepnerv.model import Generator
+    from orepnerv.utils import PositionalEncoding, adaptive_avg_pool2d, loss_fn
+    cfg = dict(embed='1.25_40', stem_dim_num='64_1', fc_hw_dim='6_8_40', expansion=4, reduction=2, lower_width=8,
+               strides=[2, 2])
+    torch.manual_seed(3)
+    pe = PositionalEncoding(cfg['embed'])
+    gen = Generator(embed_length=pe.embed_length, stem_dim_num=cfg['stem_dim_num'], fc_hw_dim=cfg['fc_hw_dim'],
+                    expansion=cfg['expansion'], num_blocks=1, norm='none', act='swish', bias=True,
+                    reduction=cfg['reduction'], conv_type='conv', stride_list=cfg['strides'], sin_res=False,
+                    lower_width=cfg['lower_width'], sigmoid=True, deploy=False, branch_type='NeRV_vanilla').to(dev)
+    assert gen.head_layers[0].in_channels == 160 and gen.head_layers[1].in_channels == 80
+    pos = torch.tensor([0.3, 0.8])
+    embed = pe(pos)
+    data = torch.rand(2, 3, 24, 32, generator=torch.Generator().manual_seed(4))
+    args = argparse.Namespace(loss_type='Fusion6')
+    outs = gen(embed)
+    targets = [adaptive_avg_pool2d(data.to(dev), x.shape[-2:]) for x in outs]
+    loss = 0.5 * loss_fn(outs[0], targets[0], args) + loss_fn(outs[1], targets[1], args)
+    loss.backward()
+    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in gen.state_dict().items()}
+    oc = dict(ocfg(cfg), sigmoid=True)
+    loss_ref, imgs_ref, _ = O.multires_loss(params, embed.cpu(), data, oc, 0.5)
+    for a, b in zip(outs, imgs_ref):
+        assert rel_l2(a, b) <= 1e-2
+    assert abs(loss.item() - loss_ref.item()) <= 3e-3
+    refs = torch.autograd.grad(loss_ref, list(params.values()))
+    for (k, p), ref in zip(gen.named_parameters(), refs):
+        err = (p.grad.cpu() - ref).norm().item()
+        assert err <= 3e-2 * ref.norm().item() + 1e-6, (k, err, ref.norm().item())
