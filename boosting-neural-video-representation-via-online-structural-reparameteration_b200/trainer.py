@@ -169,8 +169,21 @@ class FrameFitter:
         B, H, W = self.B, self.H, self.W
         if self.fold_ahead or self.adam_early:
             self._tick()        # the per-block Adam updates inside the backward need this step's lr / step count
-        check(lib.onr_frame_u8_to_f32(ptr(self.frame_u8), self.frame_u8.numel(), ptr(self.target), st), "u8_to_f32")
+        # the uint8 -> fp32 conversion of the target frame is only needed by the loss: it runs on a side stream beside
+        # the stem and the first convolutions instead of in front of them
+        main = torch.cuda.current_stream()
+        if getattr(self, "_aux_stream", None) is None:
+            self._aux_stream = torch.cuda.Stream(device=self.dev)
+        fork0 = torch.cuda.Event()
+        fork0.record(main)
+        self._aux_stream.wait_event(fork0)
+        with torch.cuda.stream(self._aux_stream):
+            check(lib.onr_frame_u8_to_f32(ptr(self.frame_u8), self.frame_u8.numel(), ptr(self.target), _lib.stream()),
+                  "u8_to_f32")
+            target_ready = torch.cuda.Event()
+            target_ready.record(self._aux_stream)
         img = self.ex.forward(t_norm=self.t_norm, freqs=self.freqs, refresh=not self.fold_ahead)
+        main.wait_event(target_ready)
         check(lib.onr_fusion_loss(ptr(img), ptr(self.target), B, H, W, self.w_l1, self.w_mse, self.w_ssim, 1.0,
                                   ptr(self.out), ptr(self.gimg), ptr(self.loss_work), st), "onr_fusion_loss")
         ms_done = None
