@@ -82,6 +82,21 @@ def record(name, payload):
         pass
 
 
+def movement_ok(tag, key, moved, moved_ref, tol):
+    """Adam normalises every update to ~lr per element, so trained tensors are compared by the MOVEMENT of each tensor:
+    ||moved - moved_ref|| <= tol * ||moved_ref||.  The measured ratio is appended to gpurun_out/movement.jsonl so the
+    tolerances in the tests can be (and were) set from measurements."""
+    err, ref = (moved - moved_ref).norm().item(), moved_ref.norm().item()
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "movement.jsonl"), "a") as f:
+            f.write(json.dumps({"test": tag, "tensor": key, "ratio": err / (ref + 1e-30), "ref_norm": ref}) + "\n")
+    except OSError:
+        pass
+    return err <= tol * ref + 1e-7
+
+
 def one_step_parity(name, dev, branch_type="ERB"):
     """Forward, Fusion6 loss and every parameter gradient of ONE full-size frame: CUDA path (reference-shaped API)
     vs the fp32 GPU oracle on the same parameters / frame.  Returns the measured errors."""

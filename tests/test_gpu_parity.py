@@ -16,9 +16,15 @@ import subprocess
 import pytest
 import torch
 
+import fullsize_util as U      # tests/ is on sys.path
 from oracle import nerv_oracle as O
 
 pytestmark = pytest.mark.gpu
+# movement of each trained tensor vs the reference / oracle (U.movement_ok).  Measured on B200 over all these tests
+# (profiles/r03_movement_ratios.jsonl): median 0.2 - 1.5 %, worst 9.2 % (tiny_erb, a 1x3 branch of 48 elements whose
+# gradient signs sit in the bf16 noise: Adam turns a sign flip into a full lr-sized step).  A wrong Adam bias correction
+# is off by 15x at step 1.
+MOVE_TOL = 0.2
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
@@ -204,7 +210,7 @@ def test_training_steps_reference_loop(dev, golden, name, bt):
     for k, v in g['trained_state'].items():
         moved_ref = v - g['init_state'][k]
         moved = sd[k].cpu() - g['init_state'][k]
-        assert (moved - moved_ref).norm().item() <= 0.35 * moved_ref.norm().item() + 1e-7, k
+        assert U.movement_ok(f"reference_loop[{name}]", k, moved, moved_ref, MOVE_TOL), k
     osd = opt.state_dict()
     assert set(osd['state'][0].keys()) == {'step', 'exp_avg', 'exp_avg_sq'}
 
@@ -232,7 +238,7 @@ def test_frame_fitter_matches_oracle_steps(dev, golden):
     for k, v in gen.state_dict().items():
         moved_ref = sd[k] - g['init_state'][k]
         moved = v.cpu() - g['init_state'][k]
-        assert (moved - moved_ref).norm().item() <= 0.35 * moved_ref.norm().item() + 1e-7, k
+        assert U.movement_ok("frame_fitter_steps", k, moved, moved_ref, MOVE_TOL), k
 
 
 # ------------------------------------------------------------------------------------------- loss / metrics

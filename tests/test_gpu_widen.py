@@ -15,9 +15,15 @@ import copy
 import pytest
 import torch
 
+import fullsize_util as U      # tests/ is on sys.path
 from oracle import nerv_oracle as O
 
 pytestmark = pytest.mark.gpu
+# movement of each trained tensor vs the reference / oracle (U.movement_ok).  Measured on B200 over all these tests
+# (profiles/r03_movement_ratios.jsonl): median 0.2 - 1.5 %, worst 9.2 % (tiny_erb, a 1x3 branch of 48 elements whose
+# gradient signs sit in the bf16 noise: Adam turns a sign flip into a full lr-sized step).  A wrong Adam bias correction
+# is off by 15x at step 1.
+MOVE_TOL = 0.2
 
 
 def rel_l2(a, b):
@@ -118,7 +124,7 @@ def test_branch_sets_frame_fitter_steps(dev, golden, name, bt):
     for k, v in gen.state_dict().items():
         moved_ref = sd[k] - g['init_state'][k]
         moved = v.cpu() - g['init_state'][k]
-        assert (moved - moved_ref).norm().item() <= 0.35 * moved_ref.norm().item() + 1e-7, k
+        assert U.movement_ok(f"branch_set_fitter[{bt}]", k, moved, moved_ref, MOVE_TOL), k
     fit.release_graph()
 
 
@@ -205,7 +211,7 @@ def test_activation_frame_fitter_gelu(dev, golden):
         assert abs(out[0].item() - loss.item()) <= 3e-3, (t, out[0].item(), loss.item())
     for k, v in gen.state_dict().items():
         moved_ref = sd[k] - init[k]
-        assert ((v.cpu() - init[k]) - moved_ref).norm().item() <= 0.35 * moved_ref.norm().item() + 1e-7, k
+        assert U.movement_ok("gelu_fitter", k, v.cpu() - init[k], moved_ref, MOVE_TOL), k
     fit.release_graph()
 
 
@@ -296,7 +302,7 @@ def test_finetune_steps_against_reference_golden(dev, golden, name):
             ref = ref * mask                                                        # weight_orig -> effective weight
         moved_ref = ref - (start[k] * mask if mask is not None else start[k])
         moved = v - (start[k] * mask if mask is not None else start[k])
-        assert (moved - moved_ref).norm().item() <= 0.35 * moved_ref.norm().item() + 1e-7, k
+        assert U.movement_ok(f"finetune[{name}]", k, moved, moved_ref, MOVE_TOL), k
 
 
 @pytest.mark.parametrize("bt", ["ERB", "NeRV_vanilla"])
@@ -427,7 +433,7 @@ def test_multires_heads_against_reference_golden(dev, golden):
     sd = gen.state_dict()
     for k, v in g['trained_state'].items():
         moved_ref = v - g['init_state'][k]
-        assert ((sd[k].cpu() - g['init_state'][k]) - moved_ref).norm().item() <= 0.35 * moved_ref.norm().item() + 1e-7, k
+        assert U.movement_ok("multires_module_loop", k, sd[k].cpu() - g['init_state'][k], moved_ref, MOVE_TOL), k
     # decode: a list with one fresh image per stage, graph replay == eager
     gen.eval()
     with torch.no_grad():
@@ -451,7 +457,6 @@ def test_reference_default_architecture_full_size(dev):
     --stem_dim_num 1024_1, --fc_hw_dim 9_16_128, --expansion 8, --lower_width 32, --strides 5 3 2 2 2 (1080p), with
     --single_res: block inputs of 128 / 1024 / 512 / 256 / 128 channels (wgrad in up to 8 channel chunks), N = 25 600 on
     block 0.  One full-size frame: image, loss and every parameter gradient against the fp32 GPU oracle."""
-    import fullsize_util as U
     from orepnerv.data import synthetic_clip
     from orepnerv.utils import loss_fn
     cfg = dict(embed='1.25_80', stem_dim_num='1024_1', fc_hw_dim='9_16_128', expansion=8, reduction=2, lower_width=32,
