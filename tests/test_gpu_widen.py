@@ -519,3 +519,24 @@ def test_multires_wide_early_stage(dev):
     for (k, p), ref in zip(gen.named_parameters(), refs):
         err = (p.grad.cpu() - ref).norm().item()
         assert err <= 3e-2 * ref.norm().item() + 1e-6, (k, err, ref.norm().item())
+
+
+@pytest.mark.parametrize("bt", ["ERB", "NeRV_vanilla"])
+def test_cli_prune_finetune_workflow(dev, tmp_path, monkeypatch, bt):
+    """The prune-then-finetune command line end to end at toy size (reference main_eval.py --finetune): main_train writes
+    model_latest.pth; main_eval --prune_ratio 0.3 --finetune --finetune_epochs 2 --quant_bit 8 prunes the train-state
+    model, fine-tunes it, deploys (ERB), quantises and decodes; the reference's log files appear.
+    (Same flow as profiles/r03_cli_finetune_smoke.py.)"""
+    from orepnerv import main_eval, main_train
+    monkeypatch.chdir(tmp_path)
+    flags = ("-e 3 --lr 0.002 -b 1 --embed 1.25_40 --stem_dim_num 64_1 --fc_hw_dim 3_4_12 --expansion 1 --reduction 2 "
+             "--lower_width 8 --strides 3 2 --single_res --loss Fusion6 --warmup 0.2 --lr_type cosine --norm none "
+             f"--act swish --branch_type {bt} --outf toy --suffix ft --dataset synthetic:6x18x24 --eval_freq 1 -p 100"
+             ).split()
+    main_train.main(flags + ['--overwrite'])
+    psnr, _ = main_eval.main(flags + ['--eval_only', '--prune_ratio', '0.3', '--quant_bit', '8', '--finetune',
+                                      '--finetune_epochs', '2'])
+    out = tmp_path / 'result' / 'toy' / 'ft'
+    assert (out / 'finetune_e2_pr0.30_q8.txt').exists() and (out / 'only_prune0.30_quant8.txt').exists()
+    assert 'global prune (train state)' in (out / 'finetune_e2_pr0.30_q8.txt').read_text()
+    assert psnr > 5.0
