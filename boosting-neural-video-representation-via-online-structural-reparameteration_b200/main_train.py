@@ -45,23 +45,60 @@ def main(argv=None):
 
 
 @torch.no_grad()
-def evaluate(model, cache, pe, args):
-    """Decode every `test_gap`-th frame with the current (train-state) model: reference main_train.py:377-438."""
-    psnrs, msssims, t_fwd = [], [], 0.0
+def evaluate(model, cache, pe, args, local_rank=0, log_path=None):
+    """Reference main_train.py:377-438: decode every `test_gap`-th frame with the current (train-state) model,
+    `--eval_fps` repeating each forward 10 times for the FPS figure (:397), per-stage PSNR / MS-SSIM against the frame
+    pooled to each stage's resolution (:421-427), the progress line of :428-436.  The MACs line of :407-417 (thop) is
+    replaced by the analytic count of the convolutions.  Returns (psnr[num_stage], msssim[num_stage],
+    decode frames/s)."""
+    from .utils import adaptive_avg_pool2d, psnr_fn
+    psnr_list, msssim_list, time_list = [], [], []
     model.eval()
-    for i in range(0, len(cache), args.test_gap):
-        embed = pe(cache.t[i:i + 1])
-        torch.cuda.synchronize()
-        t0 = time.time()
-        out = model(embed)
-        torch.cuda.synchronize()
-        t_fwd += time.time() - t0
-        target = cache.frames[i:i + 1].float().div(255)
-        psnrs.append(frame_stats(out[-1], target)[4].view(1))   # the full-resolution stage
-        msssims.append(msssim_fn(out[-1:], [target]).view(1))
+    frames = list(range(0, len(cache), args.test_gap))
+    fwd_num = 10 if getattr(args, 'eval_fps', False) else 1
+    val_psnr = val_msssim = None
+    for n, i in enumerate(frames):
+        if n > 10 and args.debug:
+            break
+        embed_input = pe(cache.t[i:i + 1])
+        data = cache.frames[i:i + 1].float().div(255)
+        for _ in range(fwd_num):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            output_list = model(embed_input)
+            torch.cuda.synchronize()
+            time_list.append(time.time() - t0)
+        if n == 0:
+            print(f"MACs: {decoder_macs(model) / 10 ** 9:.2f}G")
+        target_list = [adaptive_avg_pool2d(data, x.shape[-2:]) for x in output_list]
+        psnr_list.append(psnr_fn(output_list, target_list))
+        msssim_list.append(msssim_fn(output_list, target_list))
+        val_psnr = torch.cat(psnr_list, dim=0).mean(0)
+        val_msssim = torch.cat(msssim_list, dim=0).float().mean(0)
+        if n % args.print_freq == 0 or n == len(frames) - 1:
+            fps = fwd_num * (n + 1) / sum(time_list)
+            print_str = 'Rank:{}, Step [{}/{}], PSNR: {}, MSSSIM: {} FPS: {}'.format(
+                local_rank, n + 1, len(frames), RoundTensor(val_psnr, 2, False), RoundTensor(val_msssim, 4, False),
+                round(fps, 2))
+            print(print_str)
+            if log_path:
+                with open(log_path, 'a') as f:
+                    f.write(print_str + '\n')
     model.train()
-    n = len(psnrs)
-    return torch.cat(psnrs).mean().view(1), torch.cat(msssims).mean().view(1), n / max(t_fwd, 1e-9)
+    return val_psnr.cpu(), val_msssim.cpu(), len(time_list) / max(sum(time_list), 1e-9)
+
+
+def decoder_macs(model):
+    """Multiply-accumulates of one decoded frame (stem + block convolutions + heads): what `thop.profile` reports at
+    reference main_train.py:407-417, counted from the module shapes."""
+    macs = sum(m.in_features * m.out_features for m in model.stem if hasattr(m, 'in_features'))
+    h, w = model.fc_h, model.fc_w
+    for blk, head in zip(model.layers, model.head_layers):
+        macs += h * w * blk.out_channels * blk.ngf * 9
+        h, w = h * blk.stride, w * blk.stride
+        if head is not None:
+            macs += h * w * head.in_channels * 3
+    return macs
 
 
 def fit_epoch(fitter, cache, args, epoch, total_epochs, spe, world, rank, local_rank, log_path=None):
@@ -200,7 +237,7 @@ def train(local_rank, rank, world, args):
             'val_best_msssim': val_best_msssim, 'optimizer': optimizer.state_dict()}
 
         if (epoch + 1) % args.eval_freq == 0 or epoch > args.epochs - 10:
-            val_psnr, val_msssim, fps = evaluate(model, cache, pe, args)
+            val_psnr, val_msssim, fps = evaluate(model, cache, pe, args, local_rank, log_path if rank == 0 else None)
             if rank == 0:
                 is_val_best = bool(val_psnr[-1] > val_best_psnr)
                 val_best_psnr = val_psnr[-1] if is_val_best else val_best_psnr

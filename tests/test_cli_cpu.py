@@ -150,3 +150,47 @@ def test_cli_accepts_the_widened_rows_and_rejects_the_rest():
     with pytest.raises(SystemExit):                                         # the reference finetunes NeRV_vanilla | ERB only
         finish_args(build_parser(eval_mode=True).parse_args(base + ['--branch_type', 'DBB', '--prune_ratio', '0.4',
                                                                     '--finetune']))
+
+
+def test_evaluate_host_logic(monkeypatch, tmp_path, capsys):
+    """main_train.evaluate (reference main_train.py:377-438): frame selection by test_gap, --eval_fps repeats, per-stage
+    metrics, the reference's progress line and the analytic MACs — executed on the CPU with the device metric calls
+    replaced by the oracle (the arithmetic itself is covered by the GPU parity tests)."""
+    import argparse
+    import orepnerv.utils as U
+    from oracle import nerv_oracle as O
+    from orepnerv import main_train
+    from orepnerv.model import Generator
+    import torch.nn.functional as F
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(U, "adaptive_avg_pool2d", lambda d, size: F.adaptive_avg_pool2d(d, tuple(size)))
+    monkeypatch.setattr(U, "psnr_fn", lambda outs, tgts: torch.cat(
+        [O.psnr(o, t).view(1, 1).expand(o.size(0), -1) for o, t in zip(outs, tgts)], dim=1))
+    monkeypatch.setattr(main_train, "msssim_fn", lambda outs, tgts: torch.zeros(1, len(outs)).expand(outs[-1].size(0), -1))
+    gen = Generator(embed_length=8, stem_dim_num='16_1', fc_hw_dim='3_4_4', expansion=1, num_blocks=1, norm='none',
+                    act='swish', bias=True, reduction=2, conv_type='conv', stride_list=[2, 2], sin_res=False,
+                    lower_width=4, sigmoid=False, deploy=False, branch_type='NeRV_vanilla')
+    calls = []
+
+    def fake_forward(embed):
+        calls.append(float(embed.sum()))
+        g = torch.Generator().manual_seed(len(calls))
+        return [torch.rand(1, 3, 6, 8, generator=g), torch.rand(1, 3, 12, 16, generator=g)]
+    gen.forward = fake_forward
+
+    class Clip:
+        frames = torch.randint(0, 256, (5, 3, 12, 16), generator=torch.Generator().manual_seed(0)).to(torch.uint8)
+        t = torch.arange(5, dtype=torch.float32) / 5
+
+        def __len__(self):
+            return 5
+    args = argparse.Namespace(test_gap=2, eval_fps=True, debug=False, print_freq=1)
+    log = tmp_path / "rank0.txt"
+    psnr, msssim, fps = main_train.evaluate(gen, Clip(), lambda t: t.view(1, 1).repeat(1, 8), args, 0, str(log))
+    assert len(calls) == 3 * 10                                   # frames 0, 2, 4; --eval_fps: 10 forwards each
+    assert psnr.shape == (2,) and msssim.shape == (2,) and fps > 0 and gen.training
+    lines = log.read_text().strip().split('\n')
+    assert len(lines) == 3 and lines[-1].startswith('Rank:0, Step [3/3], PSNR: ') and ' FPS: ' in lines[-1]
+    # stem 8*16 + 16*48, blocks 3*4*16*4*9 + 6*8*16*4*9, heads 6*8*4*3 + 12*16*4*3
+    assert main_train.decoder_macs(gen) == 8 * 16 + 16 * 48 + 12 * 16 * 4 * 9 + 48 * 16 * 4 * 9 + 48 * 12 + 192 * 12
+    assert 'MACs: ' in capsys.readouterr().out
