@@ -23,8 +23,9 @@ pytestmark = pytest.mark.gpu
 # movement of each trained tensor vs the reference / oracle (U.movement_ok).  Measured on B200 over all these tests
 # (profiles/r03_movement_ratios.jsonl): median 0.2 - 1.5 %, worst 9.2 % (tiny_erb, a 1x3 branch of 48 elements whose
 # gradient signs sit in the bf16 noise: Adam turns a sign flip into a full lr-sized step).  A wrong Adam bias correction
-# is off by 15x at step 1.
-MOVE_TOL = 0.2
+# is off by 15x at step 1.  The wgrad accumulates with atomics (run-to-run noise in the last bits decides those signs), so the
+# bound keeps 2.7x headroom over the worst measured ratio.
+MOVE_TOL = 0.25
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
