@@ -17,6 +17,7 @@ import math
 import os
 
 import torch
+import torch.distributed
 
 from . import _lib, branches
 from ._lib import ConvDesc, WgradDesc, check, ptr
@@ -441,7 +442,11 @@ class NetExecutor:
         def snapshot():
             return [self._img_stage[l].clone() for l in self.head_stages[:-1]] + [self._img_static.clone()]
 
-        if os.environ.get("ONR_DECODE_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
+        # (multi-process runs keep the eager launches: a process group's watchdog thread touches the CUDA API, which a
+        # capture in the default global error mode does not tolerate)
+        multi_proc = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1
+        if os.environ.get("ONR_DECODE_GRAPH", "1") == "0" or multi_proc or torch.cuda.is_current_stream_capturing():
             img = torch.empty(self.B, 3, self.H, self.W, dtype=torch.float32, device=self.dev)
             outs = {l: torch.empty_like(self._img_stage[l]) for l in self.head_stages[:-1]}
             self.forward(embed=embed, out=img, outs=outs)
