@@ -202,3 +202,35 @@ def test_generator_multires_layout(golden):
     sd = gen.state_dict()
     assert list(sd) == list(g['init_state'])
     assert all(torch.equal(sd[k], v) for k, v in g['init_state'].items())
+
+
+@pytest.mark.parametrize("bt", ["DBB", "ECB"])
+def test_branch_fold_backward_is_linear_in_dk(hostlib, bt):
+    """The data-parallel exchange all-reduces the folded-kernel gradient dK|dbias and runs the fold backward on the sum on
+    every rank (SURVEY.md 8e option 2).  That is only right because the fold backward is linear in (dK, dbias) for fixed
+    branch parameters: bwd(dK1 + dK2) == bwd(dK1) + bwd(dK2) — checked on the kernels' own arithmetic."""
+    from orepnerv import branches
+    from orepnerv.model import NeRVBlock
+    torch.manual_seed(21)
+    cin, cout = 6, 24
+    blk = NeRVBlock(ngf=cin, new_ngf=cout, stride=1, bias=True, norm='none', act='swish', deploy=False,
+                    conv_type='conv', branch_type=bt)
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            if n.endswith('.scale') or n.endswith('.b0'):
+                p.copy_(torch.randn_like(p))
+    slots = branches.branch_slots(blk)
+    s = branches.make_branch_set(cin, cout, {slot: t.detach() for slot, _, t in slots})
+    gen = torch.Generator().manual_seed(22)
+
+    def bwd(dK, db):
+        grads = {n: torch.zeros_like(t) for _, n, t in slots if not n.endswith('.mask')}
+        gset = branches.make_branch_set(cin, cout, {slot: grads.get(n) for slot, n, _ in slots})
+        hostlib.host_branch_fold_bwd(C.byref(s), C.c_void_p(dK.data_ptr()), C.c_void_p(db.data_ptr()), C.byref(gset))
+        return grads
+
+    dK1, dK2 = torch.randn(cout, cin, 3, 3, generator=gen), torch.randn(cout, cin, 3, 3, generator=gen)
+    db1, db2 = torch.randn(cout, generator=gen), torch.randn(cout, generator=gen)
+    g1, g2, g12 = bwd(dK1, db1), bwd(dK2, db2), bwd(dK1 + dK2, db1 + db2)
+    for n in g12:
+        torch.testing.assert_close(g12[n], g1[n] + g2[n], rtol=1e-4, atol=1e-5, msg=lambda m: f"{n}: {m}")
