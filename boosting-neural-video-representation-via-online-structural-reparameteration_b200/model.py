@@ -413,7 +413,7 @@ class Generator(nn.Module):
         return self.head_layers[len(self.layers) - 1]
 
     def executor(self, batch, train):
-        key = (batch, bool(train), tuple(b.is_erb_train() for b in self.layers),
+        key = (batch, bool(train), tuple(b.fold_kind() for b in self.layers),
                str(next(self.parameters()).device))
         ex = self._executors.get(key)
         if ex is None:
