@@ -17,7 +17,8 @@ build container and stores small input/output vectors in `tests/golden/*.pt`; `t
 checks this oracle against them.  The SSIM / MS-SSIM part restates the third-party
 `pytorch_msssim==0.2.1` (reference requirements.txt:3), which is absent from /root/reference and from the
 container: **parity unpinned** for that sub-function (it is cross-checked against an independent
-float64 direct-window implementation in the tests instead).
+float64 direct-window implementation, and against the separately written stand-in of the package that the golden
+generator uses — tests/golden/_shim/pytorch_msssim.py — in the tests instead).
 """
 import math
 

@@ -1,18 +1,130 @@
-"""Stand-in for the third-party `pytorch_msssim==0.2.1` (reference requirements.txt:3), which is not
-installed in the build container.  Only used by make_golden.py so that the UNMODIFIED reference utils.py
-imports; it forwards to the oracle's restatement of the published algorithm."""
-import os
-import sys
+"""Stand-in for the third-party `pytorch_msssim==0.2.1` (reference requirements.txt:3), which is neither vendored by
+the reference nor installed in the build container (no network).  Only used by make_golden.py so that the UNMODIFIED
+reference utils.py imports.
 
-sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..", "..")))
-from oracle import nerv_oracle as _o  # noqa: E402
+It is written INDEPENDENTLY of oracle/nerv_oracle.py, following the structure of the published package
+(`_fspecial_gauss_1d`, `gaussian_filter` looping over the spatial dims with the window transposed, `_ssim`, `ssim`,
+`ms_ssim`), with the package's own defaults (win_size 11, win_sigma 1.5, K = (0.01, 0.03), no `nonnegative_ssim`),
+so the golden vectors produced through the reference's call sites (utils.py:148-187, :205) do not loop back to the
+oracle: tests/test_oracle_golden.py compares the oracle with what THIS module computed.  The real package is still
+absent — parity with it stays "unpinned" — but the two restatements are separate pieces of code.
+"""
+import warnings
+
+import torch
+import torch.nn.functional as F
 
 
-def ssim(X, Y, data_range=1, size_average=True, **kw):
-    assert data_range == 1 and size_average
-    return _o.ssim(X, Y)
+def _fspecial_gauss_1d(size, sigma):
+    coords = torch.arange(size).to(dtype=torch.float)
+    coords -= size // 2
+    g = torch.exp(-(coords ** 2) / (2 * sigma ** 2))
+    g /= g.sum()
+    return g.unsqueeze(0).unsqueeze(0)
 
 
-def ms_ssim(X, Y, data_range=1, size_average=True, **kw):
-    assert data_range == 1 and size_average
-    return _o.ms_ssim(X, Y)
+def gaussian_filter(input, win):
+    assert all(ws == 1 for ws in win.shape[1:-1]), win.shape
+    if len(input.shape) == 4:
+        conv = F.conv2d
+    elif len(input.shape) == 5:
+        conv = F.conv3d
+    else:
+        raise NotImplementedError(input.shape)
+    C = input.shape[1]
+    out = input
+    for i, s in enumerate(input.shape[2:]):
+        if s >= win.shape[-1]:
+            out = conv(out, weight=win.transpose(2 + i, -1), stride=1, padding=0, groups=C)
+        else:
+            warnings.warn(f"Skipping Gaussian Smoothing at dimension 2+{i} for input: {input.shape} and win size: "
+                          f"{win.shape[-1]}")
+    return out
+
+
+def _ssim(X, Y, data_range, win, size_average=True, K=(0.01, 0.03)):
+    K1, K2 = K
+    compensation = 1.0
+    C1 = (K1 * data_range) ** 2
+    C2 = (K2 * data_range) ** 2
+    win = win.to(X.device, dtype=X.dtype)
+    mu1 = gaussian_filter(X, win)
+    mu2 = gaussian_filter(Y, win)
+    mu1_sq = mu1.pow(2)
+    mu2_sq = mu2.pow(2)
+    mu1_mu2 = mu1 * mu2
+    sigma1_sq = compensation * (gaussian_filter(X * X, win) - mu1_sq)
+    sigma2_sq = compensation * (gaussian_filter(Y * Y, win) - mu2_sq)
+    sigma12 = compensation * (gaussian_filter(X * Y, win) - mu1_mu2)
+    cs_map = (2 * sigma12 + C2) / (sigma1_sq + sigma2_sq + C2)
+    ssim_map = ((2 * mu1_mu2 + C1) / (mu1_sq + mu2_sq + C1)) * cs_map
+    ssim_per_channel = torch.flatten(ssim_map, 2).mean(-1)
+    cs = torch.flatten(cs_map, 2).mean(-1)
+    return ssim_per_channel, cs
+
+
+def ssim(X, Y, data_range=255, size_average=True, win_size=11, win_sigma=1.5, win=None, K=(0.01, 0.03),
+         nonnegative_ssim=False):
+    if not X.shape == Y.shape:
+        raise ValueError("Input images should have the same dimensions.")
+    for d in range(len(X.shape) - 1, 1, -1):
+        X = X.squeeze(dim=d)
+        Y = Y.squeeze(dim=d)
+    if len(X.shape) not in (4, 5):
+        raise ValueError(f"Input images should be 4-d or 5-d tensors, but got {X.shape}")
+    if win is not None:
+        win_size = win.shape[-1]
+    if not (win_size % 2 == 1):
+        raise ValueError("Window size should be odd.")
+    if win is None:
+        win = _fspecial_gauss_1d(win_size, win_sigma)
+        win = win.repeat([X.shape[1]] + [1] * (len(X.shape) - 1))
+    ssim_per_channel, cs = _ssim(X, Y, data_range=data_range, win=win, size_average=False, K=K)
+    if nonnegative_ssim:
+        ssim_per_channel = torch.relu(ssim_per_channel)
+    if size_average:
+        return ssim_per_channel.mean()
+    return ssim_per_channel.mean(1)
+
+
+def ms_ssim(X, Y, data_range=255, size_average=True, win_size=11, win_sigma=1.5, win=None, weights=None,
+            K=(0.01, 0.03)):
+    if not X.shape == Y.shape:
+        raise ValueError("Input images should have the same dimensions.")
+    for d in range(len(X.shape) - 1, 1, -1):
+        X = X.squeeze(dim=d)
+        Y = Y.squeeze(dim=d)
+    if len(X.shape) == 4:
+        avg_pool = F.avg_pool2d
+    elif len(X.shape) == 5:
+        avg_pool = F.avg_pool3d
+    else:
+        raise ValueError(f"Input images should be 4-d or 5-d tensors, but got {X.shape}")
+    if win is not None:
+        win_size = win.shape[-1]
+    if not (win_size % 2 == 1):
+        raise ValueError("Window size should be odd.")
+    smaller_side = min(X.shape[-2:])
+    assert smaller_side > (win_size - 1) * (2 ** 4), \
+        "Image size should be larger than %d due to the 4 downsamplings in ms-ssim" % ((win_size - 1) * (2 ** 4))
+    if weights is None:
+        weights = [0.0448, 0.2856, 0.3001, 0.2363, 0.1333]
+    weights = torch.FloatTensor(weights).to(X.device, dtype=X.dtype)
+    if win is None:
+        win = _fspecial_gauss_1d(win_size, win_sigma)
+        win = win.repeat([X.shape[1]] + [1] * (len(X.shape) - 1))
+    levels = weights.shape[0]
+    mcs = []
+    for i in range(levels):
+        ssim_per_channel, cs = _ssim(X, Y, win=win, data_range=data_range, size_average=False, K=K)
+        if i < levels - 1:
+            mcs.append(torch.relu(cs))
+            padding = [s % 2 for s in X.shape[2:]]
+            X = avg_pool(X, kernel_size=2, padding=padding)
+            Y = avg_pool(Y, kernel_size=2, padding=padding)
+    ssim_per_channel = torch.relu(ssim_per_channel)
+    mcs_and_ssim = torch.stack(mcs + [ssim_per_channel], dim=0)
+    ms_ssim_val = torch.prod(mcs_and_ssim ** weights.view(-1, 1, 1), dim=0)
+    if size_average:
+        return ms_ssim_val.mean()
+    return ms_ssim_val.mean(1)

@@ -122,3 +122,31 @@ def test_prune_threshold_matches_torch_prune():
     for m in mods:
         assert torch.equal(m.weight_mask, (m.weight_orig.abs() > thr).float())
     assert sum(int((m.weight_mask == 0).sum()) for m in mods) == k
+
+
+def test_ssim_shim_is_a_second_independent_restatement():
+    """The golden vectors that pass through pytorch_msssim (loss, MS-SSIM metric) are produced with
+    tests/golden/_shim/pytorch_msssim.py, written after the structure of the published 0.2.1 package and WITHOUT the
+    oracle: two separate restatements must agree (the real package is absent: parity with it stays unpinned)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "_shim", "pytorch_msssim.py")
+    with open(path) as f:
+        src = f.read()
+    assert "import" in src and "from oracle" not in src and "import oracle" not in src and "nerv_oracle as" not in src
+    spec = importlib.util.spec_from_file_location("pytorch_msssim_shim", path)
+    shim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shim)
+    g = torch.Generator().manual_seed(6)
+    for shape in [(2, 3, 40, 56), (1, 3, 177, 201)]:
+        a = torch.rand(shape, generator=g)
+        b = (a + 0.1 * torch.randn(shape, generator=g)).clamp(0, 1)
+        assert abs(shim.ssim(a, b, data_range=1, size_average=True).item() - O.ssim(a, b).item()) < 1e-6
+        ar = a.clone().requires_grad_(True)
+        ao = a.clone().requires_grad_(True)
+        (1 - shim.ssim(ar, b, data_range=1, size_average=True)).backward()
+        (1 - O.ssim(ao, b)).backward()
+        torch.testing.assert_close(ar.grad, ao.grad, rtol=1e-4, atol=1e-9)
+    a = torch.rand(1, 3, 177, 201, generator=g)             # odd sizes: avg_pool2d padding = dim % 2
+    b = (a + 0.05 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    assert abs(shim.ms_ssim(a, b, data_range=1, size_average=True).item() - O.ms_ssim(a, b).item()) < 1e-6
